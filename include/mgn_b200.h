@@ -1,0 +1,177 @@
+/*
+ * mgn_b200.h - C ABI of libmgn_b200.so: the B200-native (sm_100a) Encode-Process-Decode hot
+ * path of una-auxme/MeshGraphNets.jl, i.e. the GraphNetCore.jl operations MeshGraphNets.jl calls.
+ *
+ * Drop-in boundary.  MeshGraphNets.jl (src/graph.jl, src/solve.jl, src/strategies.jl,
+ * src/MeshGraphNets.jl) is unchanged; a GraphNetCore-compatible Julia module `ccall`s these
+ * entry points (see INTEGRATION.md and julia/GraphNetCoreB200.jl).  Each entry point cites the
+ * reference interface it replaces as  file:line  relative to the MeshGraphNets.jl v0.4.1 tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  Every function returns an int32_t status
+ *     (MGN_OK == 0); the message for the last failure on the calling thread is read with
+ *     mgn_last_error().  Nothing throws or aborts across the ABI.
+ *   - Julia matrices are column-major (features, entities); the same bytes are a row-major
+ *     [entities][features] C array.  That is the layout of every tensor below.
+ *   - Pointers prefixed d_ are DEVICE pointers (CuPtr{T}); h_ are HOST pointers.  The caller
+ *     owns every tensor buffer; the library owns only the opaque handles it creates.
+ *   - `stream` is a cudaStream_t passed as void* (Julia: CUDA.stream().handle).  forward /
+ *     backward / loss / adam / normaliser calls only enqueue work on that stream: no hidden
+ *     synchronisation, no allocation - they are CUDA-graph capturable.
+ *   - Node / edge ids follow `index_base` (1 for Julia arrays, src/graph.jl:31-34).
+ *   - There is NO CPU fallback: without a CUDA device every device entry point fails with
+ *     MGN_ERR_CUDA.
+ */
+#ifndef MGN_B200_H
+#define MGN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGN_ABI_VERSION 1
+
+enum {
+  MGN_OK = 0,
+  MGN_ERR_INVALID = 1, /* bad argument (null pointer, negative size, unknown enum) */
+  MGN_ERR_CUDA = 2,    /* CUDA runtime error, message holds cudaGetErrorString */
+  MGN_ERR_INDEX = 3,   /* node id outside [index_base, index_base + N) */
+  MGN_ERR_WORKSPACE = 4, /* workspace too small / missing forward state */
+  MGN_ERR_UNSUPPORTED = 5
+};
+
+/* Arithmetic of the MLP GEMMs (the latents' master copy is always fp32). */
+enum {
+  MGN_COMPUTE_FP32 = 0, /* fp32 FMA on CUDA cores: the parity mode                      */
+  MGN_COMPUTE_BF16 = 1  /* bf16 operands, fp32 accumulate on tcgen05 tensor cores (TMEM) */
+};
+
+/* GraphNetCore.build_model(quantities, dims, outputs, mps, layer_size, hidden_layers, device),
+ * reached through GraphNetCore.load at src/MeshGraphNets.jl:282-285. */
+typedef struct mgn_model_config {
+  int32_t node_in;       /* quantities                (src/MeshGraphNets.jl:274)        */
+  int32_t edge_in;       /* dims + 1                  (src/graph.jl:51-52)              */
+  int32_t out_dim;       /* outputs                   (src/MeshGraphNets.jl:277-280)    */
+  int32_t latent;        /* layer_size, must be 128 for MGN_COMPUTE_BF16 (Args :37)     */
+  int32_t mps;           /* message passing steps     (Args :36)                        */
+  int32_t hidden_layers; /* Dense layers per MLP = hidden_layers + 2 (Args :38)         */
+  float ln_eps;          /* Lux.LayerNorm epsilon, 1e-5                                 */
+  int32_t compute_mode;  /* MGN_COMPUTE_*                                               */
+} mgn_model_config;
+
+/* One tensor of the flat Float32 parameter vector (mirrors the ComponentArray `mgn.ps` that
+ * src/strategies.jl:187 hands to ODEProblem and src/MeshGraphNets.jl:376 to Optimisers.update). */
+typedef struct mgn_param_entry {
+  char name[48];  /* e.g. "processor3.edge.dense2.weight" */
+  int64_t offset; /* element offset into the flat vector */
+  int32_t rows;   /* Julia size(.,1): out for a Dense weight */
+  int32_t cols;   /* Julia size(.,2): in for a Dense weight, 1 for vectors */
+} mgn_param_entry;
+
+typedef struct mgn_model mgn_model;
+typedef struct mgn_graph mgn_graph;
+
+/* ------------------------------------------------------------------ errors / info */
+int32_t mgn_abi_version(void);
+/* Copies the calling thread's last error message (NUL terminated) into buf. */
+int32_t mgn_last_error(char* buf, size_t n);
+/* Number of visible CUDA devices (0 and MGN_OK when the driver is absent). */
+int32_t mgn_device_count(int32_t* count);
+
+/* ------------------------------------------------------------------ graph indexing (host, integer, bit exact) */
+/* GraphNetCore.one_hot(v, depth, offset)  <- src/graph.jl:26-27.  h_out is [n][depth]. */
+int32_t mgn_one_hot(const int32_t* h_v, int64_t n, int32_t depth, int32_t offset, float* h_out);
+/* GraphNetCore.triangles_to_edges(cells)  <- src/graph.jl:30.  h_cells is [C][3]; senders /
+ * receivers need room for 6*C entries; *n_edges receives E = 2 * (#unique undirected edges). */
+int32_t mgn_triangles_to_edges(const int32_t* h_cells, int64_t n_cells, int32_t* h_senders,
+                               int32_t* h_receivers, int64_t* n_edges);
+/* GraphNetCore.parse_edges(edges)  <- src/graph.jl:38.  h_edges is [U][2]; outputs hold 2*U. */
+int32_t mgn_parse_edges(const int32_t* h_edges, int64_t n_pairs, int32_t* h_senders,
+                        int32_t* h_receivers);
+/* The 0 -> 1 based shift of src/graph.jl:31-34 / :39-42.  *shifted is set to 1 if applied. */
+int32_t mgn_shift_one_based(int32_t* h_senders, int32_t* h_receivers, int64_t n_edges,
+                            int32_t* shifted);
+/* Edge features [rel ; ||rel||]  <- src/graph.jl:35-36,49-52.  h_pos [N][dim], h_out [E][dim+1]. */
+int32_t mgn_edge_features(const float* h_pos, int64_t n_nodes, int32_t dim, const int32_t* h_senders,
+                          const int32_t* h_receivers, int64_t n_edges, int32_t index_base,
+                          float* h_out);
+
+/* ------------------------------------------------------------------ graph handle (device CSR; NEW) */
+/* Builds, on the device, the stable sort of edge ids by receiver (CSR) and by sender (CSC) that
+ * turns GraphNetCore's NNlib.scatter(+) into an atomics-free segmented sum.  d_senders /
+ * d_receivers are the FeatureGraph index vectors of src/graph.jl:87-96 (Int32, device).
+ * Synchronises `stream` once (validation of the ids).  Ids are copied; the caller may free them. */
+int32_t mgn_graph_create(int64_t n_nodes, int64_t n_edges, const int32_t* d_senders,
+                         const int32_t* d_receivers, int32_t index_base, void* stream,
+                         mgn_graph** out);
+int32_t mgn_graph_destroy(mgn_graph* g);
+int32_t mgn_graph_sizes(const mgn_graph* g, int64_t* n_nodes, int64_t* n_edges);
+/* Copies the index structures to the host for the bit-exact check against the oracle.  Any
+ * pointer may be NULL.  row_ptr/col_ptr: [N+1]; perm: CSR slot -> 0-based original edge id [E];
+ * perm_sender: CSC slot -> 0-based original edge id [E]. */
+int32_t mgn_graph_get_index(const mgn_graph* g, int32_t* h_row_ptr, int32_t* h_perm,
+                            int32_t* h_col_ptr, int32_t* h_perm_sender);
+
+/* ------------------------------------------------------------------ model */
+int32_t mgn_model_create(const mgn_model_config* cfg, mgn_model** out);
+int32_t mgn_model_destroy(mgn_model* m);
+int32_t mgn_model_param_count(const mgn_model* m, int64_t* count);
+/* Fills up to `capacity` entries (may be 0 / NULL to query) and returns the total in *n. */
+int32_t mgn_model_param_layout(const mgn_model* m, mgn_param_entry* entries, int32_t capacity,
+                               int32_t* n);
+/* Bytes of caller-owned device scratch that forward (+backward when training != 0) needs. */
+int32_t mgn_workspace_bytes(const mgn_model* m, const mgn_graph* g, int32_t training,
+                            size_t* bytes);
+
+/* `mgn.model(graph, ps, st)`  <- src/solve.jl:200 and inside step! (src/strategies.jl:421).
+ * d_nf [N][node_in] and d_ef [E][edge_in] are FeatureGraph.node_features / edge_features in
+ * the ORIGINAL edge order; d_out is [N][out_dim].  With training != 0 the activations the
+ * backward pass needs are kept in the workspace. */
+int32_t mgn_forward(const mgn_model* m, const mgn_graph* g, const float* d_params,
+                    const float* d_nf, const float* d_ef, float* d_out, void* d_workspace,
+                    size_t workspace_bytes, int32_t training, void* stream);
+
+/* Reverse mode of mgn_forward: what Zygote derives for step! (src/strategies.jl:421) and what
+ * SciMLSensitivity's ZygoteVJP asks of ode_step (src/strategies.jl:183-194).  Needs the
+ * workspace of the matching training forward.  d_dparams [P] is overwritten; d_dnf
+ * [N][node_in] (gradient w.r.t. the node features, for the NeuralODE adjoint) may be NULL. */
+int32_t mgn_backward(const mgn_model* m, const mgn_graph* g, const float* d_params,
+                     const float* d_nf, const float* d_ef, const float* d_dout,
+                     float* d_dparams, float* d_dnf, void* d_workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* Loss of GraphNetCore.step!(mgn, graph, target, mask, mse_reduce)  <- src/strategies.jl:421:
+ * loss = mean(sum_rows((target - out)^2)[mask]); d_mask holds n_mask node ids (the Int32 vector
+ * of src/MeshGraphNets.jl:352).  Writes the scalar to d_loss[0] and dloss/dout to d_dout. */
+int32_t mgn_loss_mse_masked(const float* d_out, const float* d_target, int64_t n_nodes,
+                            int32_t out_dim, const int32_t* d_mask, int64_t n_mask,
+                            int32_t index_base, float* d_loss, float* d_dout, void* stream);
+
+/* Optimisers.update with Adam  <- src/MeshGraphNets.jl:374-378.  t is the 1-based step. */
+int32_t mgn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
+                      float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
+
+/* ------------------------------------------------------------------ normalisers */
+/* NormaliserOnline state on the device: d_state = [acc_sum[F] | acc_sum_sq[F] | acc_count |
+ * num_acc] (2F+2 floats).  mgn_norm_online_update is the accumulate branch of the callable
+ * (src/graph.jl:80,84,93; src/strategies.jl:399-410); it is skipped on-device once
+ * num_acc >= max_acc.  d_x is [M][F]. */
+int32_t mgn_norm_online_update(const float* d_x, int64_t rows, int32_t features, float* d_state,
+                               float max_acc, void* stream);
+/* y = (x - mean)/std (inverse == 0) or y = x*std + mean (inverse != 0, inverse_data at
+ * src/solve.jl:207-209) from an online state.  y has leading dimension ld_y and starts at
+ * column col_y, so build_graph's vcat (src/graph.jl:80-86) is written in place. */
+int32_t mgn_norm_online_apply(const float* d_x, int64_t rows, int32_t features,
+                              const float* d_state, float std_eps, int32_t inverse, float* d_y,
+                              int32_t ld_y, int32_t col_y, void* stream);
+/* Offline normalisers and any other per-feature affine map: y = x*scale + shift. */
+int32_t mgn_affine_apply(const float* d_x, int64_t rows, int32_t features, float scale,
+                         float shift, float* d_y, int32_t ld_y, int32_t col_y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGN_B200_H */

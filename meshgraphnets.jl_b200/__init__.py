@@ -1,0 +1,16 @@
+"""meshgraphnets.jl_b200 - B200-native (sm_100a) Encode-Process-Decode hot path of MeshGraphNets.jl.
+
+csrc/            CUDA kernels + the C ABI (libmgn_b200.so, include/mgn_b200.h)
+core.py          host mirror of the GraphNetCore.jl names MeshGraphNets.jl calls
+graph.py         mirror of src/graph.jl      (create_base_graph, build_graph)
+solve.py         mirror of src/solve.jl      (ode_step, ode_func_eval, rollout)
+strategies.py    mirror of src/strategies.jl (DerivativeTraining step)
+"""
+from ._lib import COMPUTE_BF16, COMPUTE_FP32, LIB_PATH, MgnError, load  # noqa: F401
+from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, NormaliserOfflineMeanStd,  # noqa: F401
+                   NormaliserOfflineMinMax, NormaliserOnline, build_model, edge_features, init_params,
+                   inverse_data, mse_reduce, one_hot, parse_edges, shift_one_based, step_,
+                   triangles_to_edges)
+from .graph import build_graph, create_base_graph  # noqa: F401
+from .solve import ode_func_eval, ode_step, rollout  # noqa: F401
+from .strategies import DerivativeTraining, get_delta, init_train_step, train_step  # noqa: F401

@@ -1,0 +1,98 @@
+"""ctypes binding of libmgn_b200.so (include/mgn_b200.h) - the stand-in, in this Julia-less
+image, for the ``ccall`` stubs of julia/GraphNetCoreB200.jl.  There is no fallback: a missing
+library or a failing call raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmgn_b200.so")
+
+MGN_OK = 0
+COMPUTE_FP32 = 0
+COMPUTE_BF16 = 1
+
+
+class MgnError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmgn_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("node_in", C.c_int32), ("edge_in", C.c_int32), ("out_dim", C.c_int32),
+        ("latent", C.c_int32), ("mps", C.c_int32), ("hidden_layers", C.c_int32),
+        ("ln_eps", C.c_float), ("compute_mode", C.c_int32),
+    ]
+
+
+class ParamEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32)]
+
+
+_p = C.c_void_p
+_i32, _i64, _f32, _sz = C.c_int32, C.c_int64, C.c_float, C.c_size_t
+
+# name -> argtypes (every function returns int32_t)
+SIGNATURES = {
+    "mgn_abi_version": [],
+    "mgn_last_error": [C.c_char_p, _sz],
+    "mgn_device_count": [C.POINTER(_i32)],
+    "mgn_one_hot": [_p, _i64, _i32, _i32, _p],
+    "mgn_triangles_to_edges": [_p, _i64, _p, _p, C.POINTER(_i64)],
+    "mgn_parse_edges": [_p, _i64, _p, _p],
+    "mgn_shift_one_based": [_p, _p, _i64, C.POINTER(_i32)],
+    "mgn_edge_features": [_p, _i64, _i32, _p, _p, _i64, _i32, _p],
+    "mgn_graph_create": [_i64, _i64, _p, _p, _i32, _p, C.POINTER(_p)],
+    "mgn_graph_destroy": [_p],
+    "mgn_graph_sizes": [_p, C.POINTER(_i64), C.POINTER(_i64)],
+    "mgn_graph_get_index": [_p, _p, _p, _p, _p],
+    "mgn_model_create": [C.POINTER(ModelConfig), C.POINTER(_p)],
+    "mgn_model_destroy": [_p],
+    "mgn_model_param_count": [_p, C.POINTER(_i64)],
+    "mgn_model_param_layout": [_p, C.POINTER(ParamEntry), _i32, C.POINTER(_i32)],
+    "mgn_workspace_bytes": [_p, _p, _i32, C.POINTER(_sz)],
+    "mgn_forward": [_p, _p, _p, _p, _p, _p, _p, _sz, _i32, _p],
+    "mgn_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
+    "mgn_loss_mse_masked": [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p, _p],
+    "mgn_adam_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i64, _p],
+    "mgn_norm_online_update": [_p, _i64, _i32, _p, _f32, _p],
+    "mgn_norm_online_apply": [_p, _i64, _i32, _p, _f32, _i32, _p, _i32, _i32, _p],
+    "mgn_affine_apply": [_p, _i64, _i32, _f32, _f32, _p, _i32, _i32, _p],
+}
+
+_lib = None
+
+
+def load():
+    """Loads the shared library (once) and declares every prototype of include/mgn_b200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MgnError(-1, f"{LIB_PATH} is missing - run `python meshgraphnets.jl_b200/build.py` "
+                           "(there is no CPU or PyTorch fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.argtypes = args
+        fn.restype = _i32
+    _lib = lib
+    return lib
+
+
+def last_error():
+    buf = C.create_string_buffer(1024)
+    load().mgn_last_error(buf, 1024)
+    return buf.value.decode(errors="replace")
+
+
+def check(status):
+    if status != MGN_OK:
+        raise MgnError(status, last_error())
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args))

@@ -1,0 +1,155 @@
+// Internal declarations shared by the translation units of libmgn_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mgn_b200.h"
+
+namespace mgn {
+
+void set_error(const std::string& msg);
+int32_t fail(int32_t code, const std::string& msg);
+
+#define MGN_CUDA_TRY(expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::mgn::fail(MGN_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+  } while (0)
+
+#define MGN_REQUIRE(cond, msg)                                  \
+  do {                                                          \
+    if (!(cond)) return ::mgn::fail(MGN_ERR_INVALID, (msg));    \
+  } while (0)
+
+#define MGN_TRY(expr)                  \
+  do {                                 \
+    int32_t _s = (expr);               \
+    if (_s != MGN_OK) return _s;       \
+  } while (0)
+
+constexpr int kMaxDense = 8;
+
+// One MLP of the flat parameter vector: n_dense Dense layers (+ LayerNorm).
+struct MlpLayout {
+  std::string name;
+  int in_dim = 0, out_dim = 0, n_dense = 0;
+  bool layer_norm = false;
+  int64_t w_off[kMaxDense], b_off[kMaxDense];
+  int in[kMaxDense], out[kMaxDense];
+  int64_t ln_bias_off = -1, ln_scale_off = -1;
+};
+
+}  // namespace mgn
+
+struct mgn_model {
+  mgn_model_config cfg;
+  std::vector<mgn::MlpLayout> mlps;  // encoder.node, encoder.edge, (edge, node) x mps, decoder
+  int64_t n_params = 0;
+  int n_dense() const { return cfg.hidden_layers + 2; }
+};
+
+struct mgn_graph {
+  int64_t N = 0, E = 0;
+  int32_t index_base = 1;
+  // device arrays (0-based)
+  int32_t* row_ptr = nullptr;    // [N+1] CSR by receiver
+  int32_t* perm = nullptr;       // [E]   CSR slot -> original edge id (stable)
+  int32_t* send_csr = nullptr;   // [E]   sender node of CSR slot
+  int32_t* recv_csr = nullptr;   // [E]   receiver node of CSR slot
+  int32_t* col_ptr = nullptr;    // [N+1] CSC by sender
+  int32_t* perm_sender = nullptr;  // [E] CSC slot -> original edge id (stable)
+  int32_t* csc_slot = nullptr;   // [E]   CSC slot -> CSR slot of the same edge
+  int32_t max_in_degree = 0;
+};
+
+namespace mgn {
+
+// A row-concatenated, optionally gathered operand: row r of the logical matrix is
+// [seg0[idx0[r]] | seg1[idx1[r]] | seg2[idx2[r]]] (idx == nullptr -> identity).
+struct Seg {
+  const float* base;
+  const int32_t* idx;
+  int width;
+  int ld;
+};
+struct Operand {
+  Seg s[3];
+  int nseg;
+  int K() const {
+    int k = 0;
+    for (int i = 0; i < nseg; ++i) k += s[i].width;
+    return k;
+  }
+};
+
+// ---- fp32 (CUDA-core) kernels: simt_kernels.cu ------------------------------------------------
+struct LnEpilogue {          // final Dense layer: bias -> LayerNorm -> (residual)
+  const float* ln_scale;     // [n]
+  const float* ln_bias;      // [n]
+  float eps;
+  float* xhat;               // [M][n] saved normalised pre-affine values (nullable)
+  float* rstd;               // [M]    (nullable)
+  float* out;                // [M][n] LayerNorm result (nullable)
+  const float* resid_in;     // [M][n] (nullable)
+  float* resid_out;          // [M][n] = resid_in + LN (nullable)
+};
+// Y[M][n] = act(X W + b); W is [K][n] row-major (Julia (out x in) column-major).
+cudaError_t dense_forward(const Operand& x, int64_t M, const float* W, const float* bias, int n,
+                          bool relu, float* Y, const LnEpilogue* ln, cudaStream_t st);
+// dX[M][K] = dZ[M][n] W^T, optionally masked by (mask_src > 0) (ReLU of the previous layer).
+cudaError_t dense_backward_dx(const float* dZ, int64_t M, int n, const float* W, int K,
+                              const float* relu_src, float* dX, cudaStream_t st);
+// g_w[K][n] = X^T dZ and g_b[n] = colsum(dZ), written to grad (bias directly follows weight).
+// partial: scratch of dw_partial_floats(K, n, M) floats.
+size_t dw_partial_floats(int K, int n, int64_t M);
+cudaError_t dense_backward_dw(const Operand& x, const float* dZ, int64_t M, int n, float* partial,
+                              float* g_w_and_b, cudaStream_t st);
+// agg[v] = sum over CSR row v of m[j] (ascending slot = ascending original edge id).
+cudaError_t segment_sum(const float* m, const int32_t* row_ptr, int64_t N, int D, float* agg,
+                        cudaStream_t st);
+// dz = LayerNorm backward of (a[r] + b[bidx[r]]) ; column sums -> g_scale, g_bias.
+size_t ln_partial_floats(int64_t M, int D);
+cudaError_t layernorm_backward(const float* a, int lda, const float* b, int ldb,
+                               const int32_t* bidx, const float* xhat, const float* rstd,
+                               const float* scale, int64_t M, int D, float* dz, float* partial,
+                               float* g_scale, float* g_bias, cudaStream_t st);
+// d_nf[v] = base[v] + add[v] + sum_{CSR row v} dxe[j][D:2D] + sum_{CSC row v} dxe[slot][0:D]
+cudaError_t node_grad_gather(const float* base, const float* add, int ld_add, const float* dxe,
+                             const int32_t* row_ptr, const int32_t* col_ptr,
+                             const int32_t* csc_slot, int64_t N, int D, float* out,
+                             cudaStream_t st);
+// out[r][0:D] = a[r][0:D] + b[r][col_b : col_b + D]
+cudaError_t add_cols(const float* a, const float* b, int ldb, int col_b, int64_t M, int D,
+                     float* out, cudaStream_t st);
+cudaError_t loss_mse_masked(const float* out, const float* target, int64_t N, int out_dim,
+                            const int32_t* mask, int64_t n_mask, int base, float* loss,
+                            float* dout, cudaStream_t st);
+cudaError_t adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1,
+                      float b2, float eps, int64_t t, cudaStream_t st);
+cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
+                               cudaStream_t st);
+cudaError_t norm_online_apply(const float* x, int64_t rows, int F, const float* state,
+                              float std_eps, int inverse, float* y, int ld_y, int col_y,
+                              cudaStream_t st);
+cudaError_t affine_apply(const float* x, int64_t rows, int F, float scale, float shift, float* y,
+                         int ld_y, int col_y, cudaStream_t st);
+
+// ---- CSR build: csr.cu -----------------------------------------------------------------------
+int32_t build_graph_index(mgn_graph* g, const int32_t* d_senders, const int32_t* d_receivers,
+                          cudaStream_t st);
+
+// ---- orchestration: pipeline.cu --------------------------------------------------------------
+int32_t workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training, size_t* bytes);
+int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
+                cudaStream_t st);
+int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                 const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                 size_t ws_bytes, cudaStream_t st);
+
+}  // namespace mgn

@@ -1,0 +1,22 @@
+"""The package directory is named ``meshgraphnets.jl_b200`` (with a dot, after the reference repo),
+which Python cannot import by name; this loader registers it as ``meshgraphnets_jl_b200``."""
+import importlib.util
+import os
+import sys
+
+_NAME = "meshgraphnets_jl_b200"
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "meshgraphnets.jl_b200")
+
+
+def load_package():
+    if _NAME in sys.modules:
+        return sys.modules[_NAME]
+    spec = importlib.util.spec_from_file_location(_NAME, os.path.join(_DIR, "__init__.py"),
+                                                  submodule_search_locations=[_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[_NAME] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+pkg = load_package()

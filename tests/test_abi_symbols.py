@@ -1,0 +1,67 @@
+"""The C-ABI library loads on a CPU-only machine and exports every symbol include/mgn_b200.h
+declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mgn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(pkg):
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mgn_b200.h but not exported"
+
+
+def test_binding_covers_header(pkg):
+    import mgn_pkg  # noqa: F401
+    from meshgraphnets_jl_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+
+
+def test_error_convention(pkg):
+    with pytest.raises(pkg.MgnError) as e:
+        pkg.Model(9, 3, 2, 15, 4096, 2)  # latent out of range
+    assert e.value.code == 1 and "latent" in str(e.value)
+    m = pkg.Model(9, 3, 2, 15, 128, 2)
+    assert m.n_params == 2877570  # SURVEY.md 8 a15 (L = 4)
+    names = [n for n, *_ in m.param_layout()]
+    assert names[0] == "encoder.node.dense1.weight" and names[-1] == "decoder.dense4.bias"
+    assert "processor15.node.layernorm.scale" in names
+
+
+def test_param_layout_matches_oracle(pkg):
+    import mgn_oracle as orc
+    cfg = orc.ModelConfig(9, 3, 2, 128, 15, 2)
+    specs, P = orc.mlp_specs(cfg)
+    m = pkg.Model(9, 3, 2, 15, 128, 2)
+    assert P == m.n_params
+    lay = {n: (o, r, c) for n, o, r, c in m.param_layout()}
+    for s in specs:
+        for l, (w, b, i, o) in enumerate(s.dense):
+            assert lay[f"{s.name}.dense{l + 1}.weight"] == (w, o, i)
+            assert lay[f"{s.name}.dense{l + 1}.bias"] == (b, o, 1)
+        if s.ln:
+            assert lay[f"{s.name}.layernorm.bias"][0] == s.ln[0]
+            assert lay[f"{s.name}.layernorm.scale"][0] == s.ln[1]
+
+
+def test_no_device_is_an_error_not_a_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    n = ctypes.c_int32(-1)
+    assert pkg.load().mgn_device_count(ctypes.byref(n)) == 0 and n.value == 0
+    h = ctypes.c_void_p()
+    st = pkg.load().mgn_graph_create(4, 0, None, None, 1, None, ctypes.byref(h))
+    assert st == 2  # MGN_ERR_CUDA: fails loudly, nothing is computed on the CPU

@@ -1,0 +1,222 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Integer work is bit-exact; fp32 mode tolerances are stated per test
+(they bound fp32 summation-order differences against the fp64 oracle)."""
+import numpy as np
+import pytest
+import torch
+
+import mgn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def mesh(nx, ny):
+    pos, cells, nt = orc.cylinder_flow_mesh(nx, ny)
+    s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
+    return pos, cells, nt, s, r
+
+
+# ------------------------------------------------------------------ integer path: bit exact
+@pytest.mark.parametrize("shape", [(4, 3), (65, 29), (200, 150)])
+def test_csr_bit_exact(pkg, shape):
+    pos, cells, nt, s, r = mesh(*shape)
+    N = pos.shape[0]
+    gi = pkg.GraphIndex(N, dev(s), dev(r))
+    rp, perm, cp, perm_s = gi.index_arrays()
+    rp_o, perm_o = orc.build_csr(r, N)
+    cp_o, perm_so = orc.build_csr(s, N)
+    assert np.array_equal(rp, rp_o) and np.array_equal(perm, perm_o)
+    assert np.array_equal(cp, cp_o) and np.array_equal(perm_s, perm_so)
+
+
+def test_csr_random_multigraph_with_hub_and_isolated_nodes(pkg):
+    rng = np.random.default_rng(0)
+    N, E = 500, 20000
+    s = rng.integers(1, N + 1, size=E).astype(np.int32)
+    r = rng.integers(1, N + 1, size=E).astype(np.int32)
+    r[:3000] = 7          # hub: degree > 48 exercises the heapsort branch
+    r[r == 11] = 12       # node 11 has no incoming edge
+    gi = pkg.GraphIndex(N, dev(s), dev(r))
+    rp, perm, cp, perm_s = gi.index_arrays()
+    rp_o, perm_o = orc.build_csr(r, N)
+    cp_o, perm_so = orc.build_csr(s, N)
+    assert np.array_equal(rp, rp_o) and np.array_equal(perm, perm_o)
+    assert np.array_equal(cp, cp_o) and np.array_equal(perm_s, perm_so)
+
+
+def test_csr_chain_and_zero_based(pkg):
+    e = orc.create_edges_1d(1000)
+    s, r = orc.parse_edges(e)
+    gi = pkg.GraphIndex(1000, dev(s), dev(r))
+    rp, perm, _, _ = gi.index_arrays()
+    rp_o, perm_o = orc.build_csr(r, 1000)
+    assert np.array_equal(rp, rp_o) and np.array_equal(perm, perm_o)
+    gi0 = pkg.GraphIndex(1000, dev(s - 1), dev(r - 1), index_base=0)
+    rp0, perm0, _, _ = gi0.index_arrays()
+    assert np.array_equal(rp0, rp_o) and np.array_equal(perm0, perm_o)
+
+
+def test_csr_rejects_out_of_range_ids(pkg):
+    s = np.array([1, 2, 3], np.int32)
+    r = np.array([2, 3, 9], np.int32)
+    with pytest.raises(pkg.MgnError) as e:
+        pkg.GraphIndex(4, dev(s), dev(r))
+    assert e.value.code == 3
+    with pytest.raises(pkg.MgnError):
+        pkg.GraphIndex(4, dev(np.array([0, 1, 1], np.int32)), dev(np.array([1, 2, 3], np.int32)))
+
+
+def test_empty_edge_set(pkg):
+    gi = pkg.GraphIndex(5, torch.zeros(0, dtype=torch.int32, device="cuda"),
+                        torch.zeros(0, dtype=torch.int32, device="cuda"))
+    rp, perm, cp, _ = gi.index_arrays()
+    assert rp.tolist() == [0] * 6 and perm.shape == (0,)
+
+
+# ------------------------------------------------------------------ float path, fp32 mode
+def _problem(nx, ny, D, mps, node_in=9, edge_in=3, seed=0, hidden=2):
+    rng = np.random.default_rng(seed)
+    pos, cells, nt, s, r = mesh(nx, ny)
+    N, E = pos.shape[0], s.shape[0]
+    cfg = orc.ModelConfig(node_in, edge_in, 2, D, mps, hidden)
+    ps = (orc.init_params(cfg, seed=seed + 1, dtype=np.float64)
+          + 0.02 * rng.normal(size=orc.mlp_specs(cfg)[1])).astype(np.float32)
+    nf = rng.normal(size=(N, node_in)).astype(np.float32)
+    ef = rng.normal(size=(E, edge_in)).astype(np.float32)
+    tgt = rng.normal(size=(N, 2)).astype(np.float32)
+    mask = orc.node_mask(nt, [0, 5])
+    return cfg, ps, nf, ef, s, r, tgt, mask, nt
+
+
+@pytest.mark.parametrize("nx,ny,D,mps,hidden", [(5, 4, 16, 2, 2), (12, 9, 128, 3, 2), (7, 5, 32, 1, 0),
+                                                (6, 4, 128, 2, 1)])
+def test_step_matches_oracle_fp32(pkg, nx, ny, D, mps, hidden):
+    """fp32 CUDA-core mode vs the fp64 oracle: loss, output, every parameter gradient and the
+    gradient w.r.t. the node features.  Tolerance 2e-4 relative L2 (fp32 accumulation order)."""
+    cfg, ps, nf, ef, s, r, tgt, mask, _ = _problem(nx, ny, D, mps, hidden=hidden)
+    g_o, loss_o, out_o, dnf_o = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
+    model = pkg.Model(cfg.node_in, cfg.edge_in, 2, mps, D, hidden)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    out = model.forward(graph, dev(ps), training=True)
+    assert rel(out.cpu().numpy(), out_o) < 2e-5
+    mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
+    (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
+    assert abs(float(loss.cpu()) - loss_o) < 2e-5 * abs(loss_o)
+    assert rel(gs.cpu().numpy(), g_o) < 2e-4
+    # per-tensor check so that a tiny tensor (a bias) cannot hide in the global norm
+    for name, off, rows, cols in model.param_layout():
+        ref = g_o[off:off + rows * cols]
+        got = gs[off:off + rows * cols].cpu().numpy()
+        assert np.linalg.norm(got - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-7 * np.linalg.norm(g_o), name
+    # VJP w.r.t. the node features (NeuralODE adjoint)
+    out2 = model.forward(graph, dev(ps), training=True)
+    _, dout_o = orc.loss_and_dout(out_o, tgt.astype(np.float64), mask)
+    dps, dnf = model.backward(graph, dev(ps), dev(dout_o.astype(np.float32)), want_dnf=True)
+    assert rel(dnf.cpu().numpy(), dnf_o) < 2e-4
+    assert rel(dps.cpu().numpy(), g_o) < 2e-4
+    assert torch.equal(out, out2)  # deterministic: no atomics anywhere on the path
+
+
+def test_inference_forward_equals_training_forward(pkg):
+    cfg, ps, nf, ef, s, r, *_ = _problem(9, 7, 128, 4)
+    model = pkg.Model(9, 3, 2, 4, 128, 2)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    a = model.forward(graph, dev(ps), training=False)
+    b = model.forward(graph, dev(ps), training=True)
+    assert torch.equal(a, b)
+
+
+def test_edge_order_permutation_invariance(pkg):
+    """Relabelling the edges permutes the summation order inside a segment only through the stable
+    sort: outputs agree to fp32 rounding (property test, SURVEY 4 iv)."""
+    cfg, ps, nf, ef, s, r, *_ = _problem(8, 6, 64, 2)
+    rng = np.random.default_rng(3)
+    p = rng.permutation(s.shape[0])
+    model = pkg.Model(9, 3, 2, 2, 64, 2)
+    a = model.forward(pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r)), dev(ps))
+    b = model.forward(pkg.FeatureGraph(dev(nf), dev(ef[p]), dev(s[p]), dev(r[p])), dev(ps))
+    assert rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+def test_cylinder_flow_full_size_fp32(pkg):
+    """BASELINE configs[1] at full size (N=1885, E=10936, D=128, mps=15) against the fp32 numpy
+    oracle (the fp64 one takes too long for the CPU suite budget); tolerance 1e-3 on gradients -
+    both sides are fp32 with different summation orders through 15 residual blocks."""
+    cfg, ps, nf, ef, s, r, tgt, mask, _ = _problem(65, 29, 128, 15)
+    g_o, loss_o, out_o, _ = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
+    model = pkg.Model(9, 3, 2, 15, 128, 2)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
+    (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
+    assert abs(float(loss.cpu()) - loss_o) < 1e-4 * abs(loss_o)
+    assert rel(gs.cpu().numpy(), g_o) < 1e-3
+
+
+# ------------------------------------------------------------------ loss / Adam / normalisers
+def test_loss_and_adam(pkg):
+    rng = np.random.default_rng(1)
+    N = 300
+    out = rng.normal(size=(N, 2)).astype(np.float32)
+    tgt = rng.normal(size=(N, 2)).astype(np.float32)
+    mask = np.sort(rng.choice(N, 120, replace=False)).astype(np.int32) + 1
+    loss_o, dout_o = orc.loss_and_dout(out.astype(np.float64), tgt.astype(np.float64), mask)
+    import ctypes as C
+    from meshgraphnets_jl_b200.core import _ptr, _stream, call
+    d_out, d_tgt, d_mask = dev(out), dev(tgt), dev(mask)
+    loss = torch.empty(1, device="cuda")
+    dout = torch.empty_like(d_out)
+    call("mgn_loss_mse_masked", _ptr(d_out), _ptr(d_tgt), N, 2, _ptr(d_mask), 120, 1, _ptr(loss), _ptr(dout), _stream())
+    assert abs(float(loss.cpu()) - loss_o) < 1e-6 * abs(loss_o)
+    assert np.allclose(dout.cpu().numpy(), dout_o, rtol=1e-6, atol=1e-9)
+    # Adam: 3 steps against the oracle rule (fp32 both sides; 2 ulp-level tolerance)
+    P = 10007
+    p = rng.normal(size=P).astype(np.float32)
+    m = np.zeros(P, np.float32); v = np.zeros(P, np.float32)
+    opt = pkg.Adam(1e-4)
+    d_p = dev(p.copy()); state = opt.setup(d_p)
+    for t in range(1, 4):
+        g = rng.normal(size=P).astype(np.float32)
+        p, m, v = orc.adam_update(p, g, m, v, t, lr=1e-4)
+        opt.update(state, d_p, dev(g))
+    assert np.allclose(d_p.cpu().numpy(), p, rtol=0, atol=2e-7)
+    assert np.allclose(state["m"].cpu().numpy(), m, rtol=1e-6, atol=1e-9)
+
+
+def test_normalisers_match_oracle(pkg):
+    rng = np.random.default_rng(2)
+    on_o = orc.NormaliserOnline(3)
+    on_g = pkg.NormaliserOnline(3)
+    for i in range(4):
+        x = (rng.normal(size=(700 + 13 * i, 3)) * [1, 10, 0.1] + [0, 5, -2]).astype(np.float32)
+        y_o = on_o(x)
+        y_g = on_g(dev(x))
+        assert np.allclose(y_g.cpu().numpy(), y_o, rtol=2e-4, atol=2e-5)  # fp32 sum order of the statistics
+    st = on_g.state.cpu().numpy()
+    assert st[6] == on_o.acc_count and st[7] == on_o.num_acc
+    assert np.allclose(st[:3], on_o.acc_sum, rtol=1e-5)
+    z = rng.normal(size=(50, 3)).astype(np.float32)
+    assert np.allclose(on_g.inverse(dev(z)).cpu().numpy(), on_o.inverse(z), rtol=2e-4, atol=2e-5)
+    # accumulation stops at max_acc
+    lim = pkg.NormaliserOnline(1, max_acc=1)
+    lim(dev(np.array([[2.0], [4.0]], np.float32)))
+    lim(dev(np.array([[100.0]], np.float32)))
+    assert lim.state.cpu().numpy()[2] == 2.0
+    # zero-variance feature: std clamps to std_epsilon, no NaN
+    c = pkg.NormaliserOnline(1)
+    y = c(dev(np.full((10, 1), 3.0, np.float32)))
+    assert torch.isfinite(y).all()
+    mm_o, mm_g = orc.NormaliserOfflineMinMax(-1.0, 6.0, 0.0, 2.0), pkg.NormaliserOfflineMinMax(-1.0, 6.0, 0.0, 2.0)
+    x = rng.normal(size=(20, 2)).astype(np.float32)
+    assert np.allclose(mm_g(dev(x)).cpu().numpy(), mm_o(x), rtol=1e-6, atol=1e-6)
+    assert np.allclose(mm_g.inverse(dev(x)).cpu().numpy(), mm_o.inverse(x), rtol=1e-5, atol=1e-5)
+    ms_o, ms_g = orc.NormaliserOfflineMeanStd(0.5, 3.0), pkg.NormaliserOfflineMeanStd(0.5, 3.0)
+    assert np.allclose(ms_g(dev(x)).cpu().numpy(), ms_o(x), rtol=1e-6, atol=1e-6)
