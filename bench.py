@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py - the reference's headline workload on B200 (BASELINE.json): derivative-training steps
+of MeshGraphNets (15 MP steps, latent 128) on a CylinderFlow-shaped synthetic mesh (N=1885,
+E=10936), through the product's public API (build_graph -> step! -> Optimisers.update mirrors).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--mode bf16|fp32] [--batch B]
+
+One JSON line on rank 0.  metric = MP-step edges/sec inside a full train step
+(E x mps x graphs_per_step x n_gpus / step time); `train_steps_per_sec` rides along.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+MPS, LATENT, HIDDEN = 15, 128, 2
+NX, NY = 65, 29            # N = 1885, E = 10936
+T_FRAMES = 64              # synthetic trajectory frames resident per rank
+METRIC = "mp_step_edges_per_sec_train"
+UNIT = "edges/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("MGN_BENCH_MODE", "bf16"), choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MGN_BENCH_BATCH", "8")),
+                    help="time windows (graphs) per step per GPU; the reference is batch 1")
+    ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workload (shared by both arms)
+# ---------------------------------------------------------------------------------------------
+def make_workload(batch, seed=1234):
+    import mgn_oracle as orc
+    pos, cells, nt = orc.cylinder_flow_mesh(NX, NY)
+    vel = orc.synthetic_velocity(pos, T_FRAMES + 1, seed=seed)
+    N = pos.shape[0]
+    # `batch` time windows of one trajectory share the topology: block-diagonal graph
+    data = {"node_type": np.tile(nt, batch).reshape(1, -1, 1),
+            "mesh_pos": np.tile(pos, (batch, 1))[None],
+            "cells": np.concatenate([cells + b * N for b in range(batch)], axis=0)[None]}
+    return data, vel, nt, N
+
+
+def sample_frames(vel, step, batch):
+    """Window b of step s uses frame (s*batch + b) mod T; returns ([B*N,2] current, [B*N,2] next)."""
+    idx = [(step * batch + b) % T_FRAMES for b in range(batch)]
+    cur = np.concatenate([vel[i] for i in idx], axis=0)
+    nxt = np.concatenate([vel[i + 1] for i in idx], axis=0)
+    return cur, nxt
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                if r.returncode == 0 and r.stdout.strip():
+                    self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                mx = max(mx, float(row[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, row[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: torch-CPU restatement of the reference op sequence
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(batch, seconds, max_steps=None, warmup=1):
+    """Times derivative-training steps of oracle/torch_cpu_ref.py (fp32, all host threads) on the
+    same CylinderFlow-shaped workload.  Returns (edges/s, steps/s, cores, n_timed)."""
+    import mgn_oracle as orc
+    import torch_cpu_ref as tref
+    data, vel, nt, N = make_workload(batch)
+    cells = data["cells"][0]
+    s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
+    ef = torch.from_numpy(orc.edge_features(data["mesh_pos"][0], s, r))
+    onehot = torch.from_numpy(orc.one_hot(data["node_type"].reshape(-1), 7, 1))
+    cfg = orc.ModelConfig(9, 3, 2, LATENT, MPS, HIDDEN)
+    p = torch.from_numpy(orc.init_params(cfg))
+    opt = {"m": torch.zeros_like(p), "v": torch.zeros_like(p), "t": 0}
+    s0 = torch.from_numpy(s.astype(np.int64) - 1)
+    r0 = torch.from_numpy(r.astype(np.int64) - 1)
+    m0 = torch.from_numpy(orc.node_mask(data["node_type"].reshape(-1), [0, 5]).astype(np.int64) - 1)
+    cores = torch.get_num_threads()
+
+    def one(step):
+        cur, nxt = sample_frames(vel, step, batch)
+        cur, nxt = torch.from_numpy(cur), torch.from_numpy(nxt)
+        nf = torch.cat([(cur - cur.mean(0)) / cur.std(0), onehot], dim=1)  # normalise + vcat (graph.jl:75-97)
+        tgt = (nxt - cur) / 0.01
+        tgt = (tgt - tgt.mean(0)) / tgt.std(0)
+        efn = (ef - ef.mean(0)) / ef.std(0).clamp_min(1e-8)
+        return tref.train_step(cfg, p, opt, nf, efn, s0, r0, tgt, m0)
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        one(warmup + n)
+        n += 1
+        el = time.perf_counter() - t0
+        if (max_steps and n >= max_steps) or (not max_steps and el >= seconds):
+            break
+    el = time.perf_counter() - t0
+    E = s.shape[0]
+    return E * MPS * n / el, batch * n / el, cores, n, el
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    edges_s, steps_s, cores, n, el = cpu_reference(1, args.cpu_seconds, max_steps=None, warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": edges_s, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1000.0 * el / n, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "train_steps_per_sec": steps_s,
+        "config": {"workload": "cylinder_flow_train_step", "nodes": NX * NY, "edges": 10936, "latent": LATENT,
+                   "mps": MPS, "graphs_per_step": 1, "note": "reference is batch 1 (batchsize not implemented, "
+                   "src/MeshGraphNets.jl:224); Julia/GraphNetCore absent -> torch-CPU port of the same op sequence"},
+        "cpu_baseline": {"value": edges_s, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} derivative-training steps (fwd+bwd+Adam), batch 1, {el:.1f} s"},
+        "e2e": {"value": edges_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import mgn_pkg
+    pkg = mgn_pkg.pkg
+    import ctypes as C
+    from meshgraphnets_jl_b200.core import _ptr, _stream, call
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    B = args.batch
+    mode = pkg.COMPUTE_BF16 if args.mode == "bf16" else pkg.COMPUTE_FP32
+    data_h, vel, nt, N = make_workload(B)
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0, device=dev)
+    E = int(senders.shape[0])
+    model, ps, st = pkg.build_model(2 + 7, 2, 2, MPS, LATENT, HIDDEN, device=dev, compute_mode=mode)
+    mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOnline(3, dev),
+                           {"velocity": pkg.NormaliserOnline(2, dev), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
+                           {"velocity": pkg.NormaliserOnline(2, dev)})
+    import mgn_oracle as orc
+    mask = torch.from_numpy(orc.node_mask(data_h["node_type"].reshape(-1), [0, 5])).to(dev)
+    opt = pkg.Adam(1e-4)
+    opt_state = opt.setup(mgn.ps)
+    strat = pkg.DerivativeTraining()
+    meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}}, "target_features": ["velocity"]}
+
+    # resident synthetic frames: rank-specific windows
+    frames = [sample_frames(vel, s + 1000 * rank, B) for s in range(T_FRAMES // max(B, 1) + 2)]
+    d_cur = [torch.from_numpy(c).to(dev) for c, _ in frames]
+    d_nxt = [torch.from_numpy(n).to(dev) for _, n in frames]
+    h_cur = [torch.from_numpy(c).pin_memory() for c, _ in frames]
+    h_nxt = [torch.from_numpy(n).pin_memory() for _, n in frames]
+    # static device buffers that one step reads (so that the step can be captured in a CUDA graph)
+    s_cur = torch.empty_like(d_cur[0])
+    s_nxt = torch.empty_like(d_nxt[0])
+    data = {"velocity": s_cur[None], "target|velocity": s_nxt[None]}
+    loss_buf = torch.zeros(1, device=dev)
+    h_loss = torch.zeros(1).pin_memory()
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as dist
+
+    def step_body():
+        t = pkg.init_train_step(strat, (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders,
+                                        receivers, 1, mask, None))
+        gs, loss = pkg.train_step(strat, t)
+        for g in gs:
+            if distributed:
+                dist.all_reduce(g)
+                g.mul_(1.0 / world)
+            opt.update(opt_state, mgn.ps, g)
+        loss_buf.copy_(loss)
+
+    # ---- optional CUDA graph of the step (all library calls only enqueue on the current stream)
+    graph = None
+    use_graph = (not args.no_graph) and not distributed
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for i in range(2):  # warm the workspace / caches outside capture
+            s_cur.copy_(d_cur[i % len(d_cur)]); s_nxt.copy_(d_nxt[i % len(d_nxt)])
+            step_body()
+    torch.cuda.synchronize()
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            t_state = opt_state["t"]
+            with torch.cuda.graph(graph):
+                step_body()
+            opt_state["t"] = t_state  # NOTE: Adam bias correction is frozen inside the graph replay
+        except Exception as e:  # capture unsupported -> plain launches
+            print(f"[bench] CUDA graph capture failed ({e}); using plain launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # 256 MB > 126 MB L2
+
+    def run_step(i, host_inputs):
+        k = i % len(d_cur)
+        if host_inputs:
+            s_cur.copy_(h_cur[k], non_blocking=True)
+            s_nxt.copy_(h_nxt[k], non_blocking=True)
+        else:
+            s_cur.copy_(d_cur[k]); s_nxt.copy_(d_nxt[k])
+        if graph is not None:
+            graph.replay()
+        else:
+            step_body()
+        if host_inputs:
+            h_loss.copy_(loss_buf, non_blocking=True)
+
+    def timed(K, host_inputs):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for i in range(K):
+            flush.zero_()  # L2 flush between timed iterations (outside the event pair)
+            evs[i][0].record()
+            run_step(i, host_inputs)
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        ms = [a.elapsed_time(b) for a, b in evs]
+        return sum(ms) / K
+
+    for i in range(args.warmup):
+        run_step(i, False)
+    torch.cuda.synchronize()
+    with ClockSampler(local_rank) as clk:
+        ms_dev = timed(args.steps, False)
+        ms_e2e = timed(args.steps, True)
+    clocks = clk.summary()
+    if distributed:
+        tt = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(tt[0]), float(tt[1])
+    final_loss = float(loss_buf.cpu())
+
+    if rank != 0:
+        return
+    edges_per_step = E * MPS * world            # E already includes the batch (block-diagonal graph)
+    value = edges_per_step / (ms_dev * 1e-3)
+    e2e = edges_per_step / (ms_e2e * 1e-3)
+    h2d = int(s_cur.numel() * 4 + s_nxt.numel() * 4)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if mode == pkg.COMPUTE_BF16 else "f32", "data": "synthetic",
+        "train_steps_per_sec": B * world / (ms_dev * 1e-3),
+        "config": {"workload": "cylinder_flow_train_step", "nodes": NX * NY, "edges": E // B, "latent": LATENT,
+                   "mps": MPS, "hidden_layers": HIDDEN, "graphs_per_step_per_gpu": B, "parallelism": f"dp{world}",
+                   "compute_mode": args.mode, "cuda_graph": graph is not None,
+                   "l2": "flushed between timed steps (256 MB write); per-step CUDA events, max over ranks"},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "clocks": clocks, "final_loss": final_loss,
+    }
+    def plain_step():
+        s_cur.copy_(d_cur[0]); s_nxt.copy_(d_nxt[0])
+        step_body()
+    line.update(extra_measurements(args, pkg, model, mgn, E, B, dev, plain_step, N * B))
+    line["gpu_launches"] = line.get("gpu_launches_per_step", 0) * args.steps
+    print(json.dumps(line), flush=True)
+
+
+def extra_measurements(args, pkg, model, mgn, E, B, dev, step_fn, n_nodes):
+    """gpu_launches, roofline of the dominant kernel, and the CPU baseline (rank 0, N=1 only)."""
+    out = {}
+    try:
+        from bench_roofline import roofline_and_launches
+        out.update(roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn, n_nodes))
+    except Exception as e:  # never lose the main line
+        out["roofline_error"] = repr(e)
+    if args.gpus == 1:
+        try:
+            edges_s, steps_s, cores, n, el = cpu_reference(1, args.cpu_seconds)
+            out["cpu_baseline"] = {"value": edges_s, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{n} batch-1 derivative-training steps (fwd+bwd+Adam) of the torch-CPU "
+                                             f"port, {el:.1f} s", "train_steps_per_sec": steps_s}
+        except Exception as e:
+            out["cpu_baseline_error"] = repr(e)
+    return out
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

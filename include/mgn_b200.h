@@ -154,6 +154,23 @@ int32_t mgn_loss_mse_masked(const float* d_out, const float* d_target, int64_t n
 int32_t mgn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
                       float lr, float beta1, float beta2, float eps, int64_t t, void* stream);
 
+/* Same update with the step counter on the device, so that a whole training step can be replayed
+ * as a CUDA graph: d_state16 is 16 bytes {int64 step; float c1; float c2}, zero-initialised by the
+ * caller; each call increments step and uses t = step. */
+int32_t mgn_adam_step_device(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
+                             float lr, float beta1, float beta2, float eps, void* d_state16,
+                             void* stream);
+
+/* ------------------------------------------------------------------ measurement hooks (bench.py) */
+/* Counts every kernel launch of the library and brackets the launches of one kernel family
+ * (`tag`, see mgn_profile_tag_name; -1 = count only) with CUDA events on their own stream.
+ * mgn_profile_end synchronises the device and returns the launch count, the number of tagged
+ * launches and the sum of their device durations.  Not for use under CUDA-graph capture. */
+int32_t mgn_profile_begin(int32_t tag);
+int32_t mgn_profile_end(int64_t* n_launches, int64_t* n_tagged, float* tagged_ms, int64_t* per_tag,
+                        int32_t per_tag_capacity);
+int32_t mgn_profile_tag_name(int32_t tag, char* buf, size_t n);
+
 /* ------------------------------------------------------------------ normalisers */
 /* NormaliserOnline state on the device: d_state = [acc_sum[F] | acc_sum_sq[F] | acc_count |
  * num_acc] (2F+2 floats).  mgn_norm_online_update is the accumulate branch of the callable

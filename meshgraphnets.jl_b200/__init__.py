@@ -9,7 +9,8 @@ strategies.py    mirror of src/strategies.jl (DerivativeTraining step)
 from ._lib import COMPUTE_BF16, COMPUTE_FP32, LIB_PATH, MgnError, load  # noqa: F401
 from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, NormaliserOfflineMeanStd,  # noqa: F401
                    NormaliserOfflineMinMax, NormaliserOnline, build_model, edge_features, init_params,
-                   inverse_data, mse_reduce, one_hot, parse_edges, shift_one_based, step_,
+                   inverse_data, mse_reduce, one_hot, parse_edges, profile_begin, profile_end, profile_tag,
+                   shift_one_based, step_,
                    triangles_to_edges)
 from .graph import build_graph, create_base_graph  # noqa: F401
 from .solve import ode_func_eval, ode_step, rollout  # noqa: F401

@@ -58,6 +58,10 @@ SIGNATURES = {
     "mgn_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
     "mgn_loss_mse_masked": [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p, _p],
     "mgn_adam_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i64, _p],
+    "mgn_adam_step_device": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p],
+    "mgn_profile_begin": [_i32],
+    "mgn_profile_end": [C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_f32), C.POINTER(_i64), _i32],
+    "mgn_profile_tag_name": [_i32, C.c_char_p, _sz],
     "mgn_norm_online_update": [_p, _i64, _i32, _p, _f32, _p],
     "mgn_norm_online_apply": [_p, _i64, _i32, _p, _f32, _i32, _p, _i32, _i32, _p],
     "mgn_affine_apply": [_p, _i64, _i32, _f32, _f32, _p, _i32, _i32, _p],

@@ -148,11 +148,13 @@ def graph_index_for(n_nodes, senders, receivers, index_base=1):
     key = (senders.data_ptr(), receivers.data_ptr(), int(n_nodes), int(senders.shape[0]), index_base)
     hit = _graph_cache.get(key)
     if hit is None:
-        if len(_graph_cache) > 64:
+        if len(_graph_cache) > 16:
             _graph_cache.clear()
-        hit = GraphIndex(n_nodes, senders, receivers, index_base)
+        # the entry keeps the index tensors alive, so their addresses cannot be recycled for a
+        # different edge list while the entry exists
+        hit = (GraphIndex(n_nodes, senders, receivers, index_base), senders, receivers)
         _graph_cache[key] = hit
-    return hit
+    return hit[0]
 
 
 @dataclass
@@ -395,11 +397,44 @@ class Adam:
         self.eta, self.beta, self.epsilon = float(eta), (float(beta[0]), float(beta[1])), float(epsilon)
 
     def setup(self, ps):
-        return {"m": torch.zeros_like(ps), "v": torch.zeros_like(ps), "t": 0}
+        # "dev" = {int64 step; float c1; float c2}: the step counter lives on the device so that a
+        # whole training step can be replayed as a CUDA graph
+        return {"m": torch.zeros_like(ps), "v": torch.zeros_like(ps), "t": 0,
+                "dev": torch.zeros(2, dtype=torch.int64, device=ps.device)}
 
     def update(self, state, ps, gs):
         """In place on ps / state (Optimisers.update returns new objects; same values)."""
         state["t"] += 1
-        call("mgn_adam_step", _ptr(ps), _ptr(gs), _ptr(state["m"]), _ptr(state["v"]), ps.numel(), self.eta,
-             self.beta[0], self.beta[1], self.epsilon, state["t"], _stream())
+        call("mgn_adam_step_device", _ptr(ps), _ptr(gs), _ptr(state["m"]), _ptr(state["v"]), ps.numel(),
+             self.eta, self.beta[0], self.beta[1], self.epsilon, _ptr(state["dev"]), _stream())
         return state, ps
+
+
+def profile_begin(tag=-1):
+    """Starts counting the library's kernel launches (and timing the family `tag`)."""
+    call("mgn_profile_begin", int(tag))
+
+
+def profile_end():
+    """-> (launches, tagged launches, tagged ms, {family name: launches})."""
+    n, k, ms = C.c_int64(0), C.c_int64(0), C.c_float(0)
+    per = (C.c_int64 * 32)()
+    call("mgn_profile_end", C.byref(n), C.byref(k), C.byref(ms), per, 32)
+    names = {}
+    buf = C.create_string_buffer(64)
+    for i in range(32):
+        if _lib.load().mgn_profile_tag_name(i, buf, 64) != 0:
+            break
+        if per[i]:
+            names[buf.value.decode()] = int(per[i])
+    return n.value, k.value, ms.value, names
+
+
+def profile_tag(name):
+    buf = C.create_string_buffer(64)
+    for i in range(32):
+        if _lib.load().mgn_profile_tag_name(i, buf, 64) != 0:
+            break
+        if buf.value.decode() == name:
+            return i
+    raise KeyError(name)

@@ -19,6 +19,44 @@ int32_t fail(int32_t code, const std::string& msg) {
   return code;
 }
 
+// ---- profiler --------------------------------------------------------------------------------
+static const char* kTagNames[TAG_COUNT] = {
+    "simt_gemm_fwd", "simt_gemm_dx", "simt_dw", "reduce_partials", "segment_sum", "ln_bwd", "ln_reduce",
+    "node_grad_gather", "add_cols", "loss", "adam", "normaliser", "tc_pack", "tc_mlp_fwd", "tc_mlp_bwd",
+    "tc_dw", "tc_misc"};
+const char* tag_name(int tag) { return tag >= 0 && tag < TAG_COUNT ? kTagNames[tag] : "?"; }
+
+struct Profiler {
+  bool on = false;
+  int tag = -1;
+  int64_t launches = 0;
+  int64_t per_tag[TAG_COUNT] = {};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+};
+static Profiler g_prof;
+
+ProfScope::ProfScope(int tag, cudaStream_t s) : st(s), slot(-1) {
+  if (!g_prof.on) return;
+  ++g_prof.launches;
+  if (tag >= 0 && tag < TAG_COUNT) ++g_prof.per_tag[tag];
+  if (tag != g_prof.tag) return;
+  std::pair<cudaEvent_t, cudaEvent_t> ev;
+  if (!g_prof.pool.empty()) {
+    ev = g_prof.pool.back();
+    g_prof.pool.pop_back();
+  } else {
+    cudaEventCreate(&ev.first);
+    cudaEventCreate(&ev.second);
+  }
+  cudaEventRecord(ev.first, st);
+  slot = (int)g_prof.events.size();
+  g_prof.events.push_back(ev);
+}
+ProfScope::~ProfScope() {
+  if (slot >= 0) cudaEventRecord(g_prof.events[slot].second, st);
+}
+
 static void add_mlp(mgn_model* m, const std::string& name, int in_dim, int out_dim, bool ln,
                     int64_t& off) {
   MlpLayout L;
@@ -337,6 +375,51 @@ int32_t mgn_adam_step(float* d_params, const float* d_grads, float* d_m, float* 
   MGN_CUDA_TRY(adam_step(d_params, d_grads, d_m, d_v, n, lr, beta1, beta2, eps, t,
                          static_cast<cudaStream_t>(stream)));
   return MGN_OK;
+}
+
+int32_t mgn_adam_step_device(float* d_params, const float* d_grads, float* d_m, float* d_v, int64_t n,
+                             float lr, float beta1, float beta2, float eps, void* d_state16,
+                             void* stream) {
+  MGN_REQUIRE(d_params && d_grads && d_m && d_v && d_state16, "adam_device: null argument");
+  MGN_REQUIRE(n >= 0, "adam_device: bad n");
+  MGN_CUDA_TRY(adam_step_device(d_params, d_grads, d_m, d_v, n, lr, beta1, beta2, eps, d_state16,
+                                static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_profile_begin(int32_t tag) {
+  MGN_REQUIRE(tag >= -1 && tag < TAG_COUNT, "profile_begin: unknown tag");
+  g_prof.on = true;
+  g_prof.tag = tag;
+  g_prof.launches = 0;
+  for (auto& c : g_prof.per_tag) c = 0;
+  for (auto& e : g_prof.events) g_prof.pool.push_back(e);
+  g_prof.events.clear();
+  return MGN_OK;
+}
+
+int32_t mgn_profile_end(int64_t* n_launches, int64_t* n_tagged, float* tagged_ms, int64_t* per_tag,
+                        int32_t per_tag_capacity) {
+  g_prof.on = false;
+  MGN_CUDA_TRY(cudaDeviceSynchronize());
+  float total = 0.f;
+  for (auto& e : g_prof.events) {
+    float ms = 0.f;
+    MGN_CUDA_TRY(cudaEventElapsedTime(&ms, e.first, e.second));
+    total += ms;
+  }
+  if (n_launches) *n_launches = g_prof.launches;
+  if (n_tagged) *n_tagged = (int64_t)g_prof.events.size();
+  if (tagged_ms) *tagged_ms = total;
+  if (per_tag)
+    for (int i = 0; i < per_tag_capacity && i < TAG_COUNT; ++i) per_tag[i] = g_prof.per_tag[i];
+  return MGN_OK;
+}
+
+int32_t mgn_profile_tag_name(int32_t tag, char* buf, size_t n) {
+  MGN_REQUIRE(buf && n > 0, "profile_tag_name: null buffer");
+  std::snprintf(buf, n, "%s", tag >= 0 && tag < TAG_COUNT ? tag_name(tag) : "");
+  return tag >= 0 && tag < TAG_COUNT ? MGN_OK : MGN_ERR_INVALID;
 }
 
 int32_t mgn_norm_online_update(const float* d_x, int64_t rows, int32_t features, float* d_state,

@@ -34,6 +34,20 @@ int32_t fail(int32_t code, const std::string& msg);
 
 constexpr int kMaxDense = 8;
 
+// ---- launch counter / per-kernel-family device timer (mgn_profile_begin / mgn_profile_end) ------
+enum KernelTag : int {
+  TAG_SIMT_GEMM_FWD = 0, TAG_SIMT_GEMM_DX, TAG_SIMT_DW, TAG_REDUCE_PARTIALS, TAG_SEGMENT_SUM,
+  TAG_LN_BWD, TAG_LN_REDUCE, TAG_NODE_GRAD_GATHER, TAG_ADD_COLS, TAG_LOSS, TAG_ADAM, TAG_NORM,
+  TAG_TC_PACK, TAG_TC_MLP_FWD, TAG_TC_MLP_BWD, TAG_TC_DW, TAG_TC_MISC, TAG_COUNT
+};
+const char* tag_name(int tag);
+struct ProfScope {  // records a CUDA event pair around one launch when its family is being timed
+  cudaStream_t st;
+  int slot;
+  ProfScope(int tag, cudaStream_t st);
+  ~ProfScope();
+};
+
 // One MLP of the flat parameter vector: n_dense Dense layers (+ LayerNorm).
 struct MlpLayout {
   std::string name;
@@ -131,6 +145,8 @@ cudaError_t loss_mse_masked(const float* out, const float* target, int64_t N, in
                             float* dout, cudaStream_t st);
 cudaError_t adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1,
                       float b2, float eps, int64_t t, cudaStream_t st);
+cudaError_t adam_step_device(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                             float b1, float b2, float eps, void* state16, cudaStream_t st);
 cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
                                cudaStream_t st);
 cudaError_t norm_online_apply(const float* x, int64_t rows, int F, const float* state,

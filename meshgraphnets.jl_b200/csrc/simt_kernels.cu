@@ -597,6 +597,30 @@ __global__ void affine_kernel(const float* __restrict__ x, int64_t rows, int F, 
   y[r * ld_y + col_y + f] = x[i] * scale + shift;
 }
 
+struct AdamState {
+  long long step;
+  float c1, c2;
+};
+__global__ void adam_tick_kernel(AdamState* s, float b1, float b2) {
+  const long long t = s->step + 1;
+  s->step = t;
+  s->c1 = (float)(1.0 - pow((double)b1, (double)t));
+  s->c2 = (float)(1.0 - pow((double)b2, (double)t));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                float b1, float b2, float eps, const AdamState* __restrict__ s) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float c1 = s->c1, c2 = s->c2;
+  const float gi = g[i];
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  p[i] = p[i] - (mi / c1) / (sqrtf(vi / c2) + eps) * lr;
+}
+
 OperandDev to_dev(const Operand& x) {
   OperandDev d{};
   d.nseg = x.nseg;
@@ -628,8 +652,9 @@ cudaError_t dense_forward(const Operand& x, int64_t M, const float* W, const flo
     l = {ln->ln_scale, ln->ln_bias, ln->eps, ln->xhat, ln->rstd, ln->out, ln->resid_in, ln->resid_out};
   }
   dim3 grid(blocks_for(M, BM), blocks_for(n, BN));
+  { ProfScope ps(TAG_SIMT_GEMM_FWD, st);
   gemm_kernel<false><<<grid, NT, 0, st>>>(xd, M, W, n, n, bias, relu ? 1 : 0, nullptr, Y, n, l,
-                                          ln ? 1 : 0);
+                                          ln ? 1 : 0); }
   return cudaGetLastError();
 }
 
@@ -643,7 +668,8 @@ cudaError_t dense_backward_dx(const float* dZ, int64_t M, int n, const float* W,
   LnDev l{};
   dim3 grid(blocks_for(M, BM), blocks_for(K, BN));
   // reduction dim = n, output columns = K, B[k][c] = W[c*n + k]
-  gemm_kernel<true><<<grid, NT, 0, st>>>(xd, M, W, n, K, nullptr, 0, relu_src, dX, K, l, 0);
+  { ProfScope ps(TAG_SIMT_GEMM_DX, st);
+  gemm_kernel<true><<<grid, NT, 0, st>>>(xd, M, W, n, K, nullptr, 0, relu_src, dX, K, l, 0); }
   return cudaGetLastError();
 }
 
@@ -671,15 +697,18 @@ cudaError_t dense_backward_dw(const Operand& x, const float* dZ, int64_t M, int 
   }
   const int nsplit = dw_nsplit(M);
   dim3 grid(blocks_for(K + 1, DW_BI), nsplit, blocks_for(n, BN));
-  dw_kernel<<<grid, NT, 0, st>>>(xd, dZ, M, n, dw_rows_per_split(M), partial);
-  reduce_partials_kernel<<<blocks_for(count, 256), 256, 0, st>>>(partial, nsplit, count, g_w_and_b);
+  { ProfScope ps(TAG_SIMT_DW, st);
+  dw_kernel<<<grid, NT, 0, st>>>(xd, dZ, M, n, dw_rows_per_split(M), partial); }
+  { ProfScope ps(TAG_REDUCE_PARTIALS, st);
+  reduce_partials_kernel<<<blocks_for(count, 256), 256, 0, st>>>(partial, nsplit, count, g_w_and_b); }
   return cudaGetLastError();
 }
 
 cudaError_t segment_sum(const float* m, const int32_t* row_ptr, int64_t N, int D, float* agg,
                         cudaStream_t st) {
   if (N == 0) return cudaSuccess;
-  segment_sum_kernel<<<blocks_for(N, 8), 256, 0, st>>>(m, row_ptr, N, D, agg);
+  { ProfScope ps(TAG_SEGMENT_SUM, st);
+  segment_sum_kernel<<<blocks_for(N, 8), 256, 0, st>>>(m, row_ptr, N, D, agg); }
   return cudaGetLastError();
 }
 
@@ -694,10 +723,13 @@ cudaError_t layernorm_backward(const float* a, int lda, const float* b, int ldb,
                                float* g_scale, float* g_bias, cudaStream_t st) {
   if (D > 128) return cudaErrorInvalidValue;
   const int64_t nblk = M > 0 ? blocks_for(M, LN_ROWS_PER_BLOCK) : 0;
-  if (nblk)
+  if (nblk) {
+    ProfScope ps(TAG_LN_BWD, st);
     ln_bwd_kernel<<<(unsigned)nblk, 256, 0, st>>>(a, lda, b, ldb, bidx, xhat, rstd, scale, M, D, dz,
                                                   partial);
-  ln_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, D, g_scale, g_bias);
+  }
+  { ProfScope ps(TAG_LN_REDUCE, st);
+  ln_reduce_kernel<<<1, 256, 0, st>>>(partial, nblk, D, g_scale, g_bias); }
   return cudaGetLastError();
 }
 
@@ -706,21 +738,24 @@ cudaError_t node_grad_gather(const float* base, const float* add, int ld_add, co
                              const int32_t* csc_slot, int64_t N, int D, float* out,
                              cudaStream_t st) {
   if (N == 0) return cudaSuccess;
+  { ProfScope ps(TAG_NODE_GRAD_GATHER, st);
   node_grad_gather_kernel<<<blocks_for(N, 8), 256, 0, st>>>(base, add, ld_add, dxe, row_ptr, col_ptr,
-                                                            csc_slot, N, D, out);
+                                                            csc_slot, N, D, out); }
   return cudaGetLastError();
 }
 
 cudaError_t add_cols(const float* a, const float* b, int ldb, int col_b, int64_t M, int D,
                      float* out, cudaStream_t st) {
   if (M == 0) return cudaSuccess;
-  add_cols_kernel<<<blocks_for(M * D, 256), 256, 0, st>>>(a, b, ldb, col_b, M, D, out);
+  { ProfScope ps(TAG_ADD_COLS, st);
+  add_cols_kernel<<<blocks_for(M * D, 256), 256, 0, st>>>(a, b, ldb, col_b, M, D, out); }
   return cudaGetLastError();
 }
 
 cudaError_t loss_mse_masked(const float* out, const float* target, int64_t N, int out_dim,
                             const int32_t* mask, int64_t n_mask, int base, float* loss,
                             float* dout, cudaStream_t st) {
+  ProfScope ps(TAG_LOSS, st);
   zero_kernel<<<blocks_for(N * out_dim, 256), 256, 0, st>>>(dout, N * out_dim);
   loss_kernel<<<1, 1024, 0, st>>>(out, target, out_dim, mask, n_mask, base, loss, dout);
   return cudaGetLastError();
@@ -732,13 +767,24 @@ cudaError_t adam_step(float* p, const float* g, float* m, float* v, int64_t n, f
   // difference is below 1 ulp of the step for t < 1e6)
   const float c1 = (float)(1.0 - pow((double)b1, (double)t));
   const float c2 = (float)(1.0 - pow((double)b2, (double)t));
-  adam_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, c1, c2);
+  { ProfScope ps(TAG_ADAM, st);
+  adam_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, c1, c2); }
+  return cudaGetLastError();
+}
+
+cudaError_t adam_step_device(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                             float b1, float b2, float eps, void* state16, cudaStream_t st) {
+  ProfScope ps(TAG_ADAM, st);
+  AdamState* s = static_cast<AdamState*>(state16);
+  adam_tick_kernel<<<1, 1, 0, st>>>(s, b1, b2);
+  adam_dev_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, s);
   return cudaGetLastError();
 }
 
 cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
                                cudaStream_t st) {
-  norm_update_kernel<<<1, 1024, 0, st>>>(x, rows, F, state, max_acc);
+  { ProfScope ps(TAG_NORM, st);
+  norm_update_kernel<<<1, 1024, 0, st>>>(x, rows, F, state, max_acc); }
   return cudaGetLastError();
 }
 
@@ -746,15 +792,17 @@ cudaError_t norm_online_apply(const float* x, int64_t rows, int F, const float* 
                               float std_eps, int inverse, float* y, int ld_y, int col_y,
                               cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
+  { ProfScope ps(TAG_NORM, st);
   norm_apply_kernel<<<blocks_for(rows * F, 256), 256, 0, st>>>(x, rows, F, state, std_eps, inverse, y,
-                                                               ld_y, col_y);
+                                                               ld_y, col_y); }
   return cudaGetLastError();
 }
 
 cudaError_t affine_apply(const float* x, int64_t rows, int F, float scale, float shift, float* y,
                          int ld_y, int col_y, cudaStream_t st) {
   if (rows == 0) return cudaSuccess;
-  affine_kernel<<<blocks_for(rows * F, 256), 256, 0, st>>>(x, rows, F, scale, shift, y, ld_y, col_y);
+  { ProfScope ps(TAG_NORM, st);
+  affine_kernel<<<blocks_for(rows * F, 256), 256, 0, st>>>(x, rows, F, scale, shift, y, ld_y, col_y); }
   return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@ Tsit5 driver itself is OrdinaryDiffEq's (out of scope); tsit5_step below restate
 Tsit5 step so that the 6-RHS-evaluations-per-step workload of config 3 can be timed."""
 from __future__ import annotations
 
+import numpy as np
 import torch
 
 from .graph import build_graph
@@ -33,10 +34,11 @@ def ode_func_eval(x, p, t):
     """src/solve.jl:147-158: overwrite the inflow nodes from data, then ode_step."""
     (mgn, ps, data, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
      receivers, val_mask, inflow_mask, saves_dt) = p
-    if inflow_mask is not None and bool(inflow_mask.any()):
-        idx = int(t / saves_dt)  # floor(Int, t / saves_dt) + 1, 0-based here
+    if inflow_mask is not None:
+        # floor(Int, t / saves_dt) + 1 with Float32 t and saves_dt (0-based here)
+        idx = int(np.floor(np.float32(t) / np.float32(saves_dt)))
         cur = torch.cat([data[f][idx] for f in target_fields], dim=1)
-        x = torch.where(inflow_mask, cur, x)
+        x.copy_(torch.where(inflow_mask, cur, x))  # in place: the reference mutates the solver state
     return ode_step(x, (mgn, ps, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats,
                         senders, receivers, val_mask), t)
 
@@ -53,7 +55,7 @@ def rollout(mgn, initial_state, fields, meta, target_fields, target_dict, node_t
     step = euler_step if solver == "euler" else tsit5_step
     n_steps = len(saves) - 1
     for i in range(n_steps):
-        t = start + i * dt
+        t = np.float32(saves[i])  # tstops = saves: the integrator lands on the save times
         x = step(lambda xx, tt: ode_func_eval(xx, p, tt), x, t, dt)
         sol.append(x.clone())
         ts.append(float(saves[i + 1]))

@@ -494,14 +494,19 @@ def ode_step(cfg, params, x, n_norms, e_norm, o_norms, fields, target_fields, ta
     return (buf * vmask).astype(x.dtype)
 
 
-def rollout_euler(rhs, x0, n_steps, dt, inflow_fn=None):
+def inflow_index(t, saves_dt):
+    """src/solve.jl:151: floor(Int, t / saves_dt) + 1 in Float32 (returned 0-based)."""
+    return int(np.floor(np.float32(t) / np.float32(saves_dt)))
+
+
+def rollout_euler(rhs, x0, saves, dt, inflow_fn=None):
     """src/solve.jl:42-68 with ``solve(prob, Euler(); adaptive=false, dt=dt, saveat=saves)``
-    (the examples/cylinder_flow/cylinder_flow.jl:79-84 configuration): returns the n_steps+1
-    saved states.  ``inflow_fn(x, t)`` applies the in-place overwrite of src/solve.jl:151."""
+    (the examples/cylinder_flow/cylinder_flow.jl:79-84 configuration): returns the saved
+    states at ``saves``.  ``inflow_fn(x, t)`` applies the in-place overwrite of src/solve.jl:151."""
     x = np.array(x0, copy=True)
     sol = [x.copy()]
-    for i in range(n_steps):
-        t = np.float32(i) * np.float32(dt)
+    for i in range(len(saves) - 1):
+        t = np.float32(saves[i])
         if inflow_fn is not None:
             x = inflow_fn(x, t)
         x = (x + np.float32(dt) * rhs(x, t)).astype(x0.dtype)
