@@ -8,6 +8,7 @@
 #include <unordered_set>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace mgn {
 
@@ -240,6 +241,8 @@ int32_t mgn_graph_destroy(mgn_graph* g) {
   cudaFree(g->col_ptr);
   cudaFree(g->perm_sender);
   cudaFree(g->csc_slot);
+  cudaFree(g->tile_row_start);
+  cudaFree(g->tile_node_start);
   delete g;
   return MGN_OK;
 }
@@ -292,11 +295,19 @@ int32_t mgn_model_create(const mgn_model_config* cfg, mgn_model** out) {
   }
   add_mlp(m, "decoder", D, cfg->out_dim, false, off);
   m->n_params = off;
+  if (cfg->compute_mode == MGN_COMPUTE_BF16) {
+    const int32_t s = tc_model_init(m);
+    if (s != MGN_OK) {
+      mgn_model_destroy(m);
+      return s;
+    }
+  }
   *out = m;
   return MGN_OK;
 }
 
 int32_t mgn_model_destroy(mgn_model* m) {
+  if (m) tc_model_free(m);
   delete m;
   return MGN_OK;
 }

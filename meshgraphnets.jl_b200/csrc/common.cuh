@@ -60,8 +60,11 @@ struct MlpLayout {
 
 }  // namespace mgn
 
+namespace mgn { namespace tc { struct ModelImages; } }
+
 struct mgn_model {
   mgn_model_config cfg;
+  mgn::tc::ModelImages* images = nullptr;  // packed-weight image plan (MGN_COMPUTE_BF16)
   std::vector<mgn::MlpLayout> mlps;  // encoder.node, encoder.edge, (edge, node) x mps, decoder
   int64_t n_params = 0;
   int n_dense() const { return cfg.hidden_layers + 2; }
@@ -79,6 +82,12 @@ struct mgn_graph {
   int32_t* perm_sender = nullptr;  // [E] CSC slot -> original edge id (stable)
   int32_t* csc_slot = nullptr;   // [E]   CSC slot -> CSR slot of the same edge
   int32_t max_in_degree = 0;
+  // node-aligned 128-row tiles of the CSR edge list (tensor-core path): tile t holds the CSR slots
+  // [tile_row_start[t], tile_row_start[t+1]) = all in-edges of nodes [tile_node_start[t], ..[t+1])
+  int32_t* tile_row_start = nullptr;   // [n_edge_tiles + 1]
+  int32_t* tile_node_start = nullptr;  // [n_edge_tiles + 1]
+  int32_t n_edge_tiles = 0;
+  bool tiles_ok = false;               // false when a node has more than 128 in-edges
 };
 
 namespace mgn {

@@ -215,6 +215,35 @@ int32_t build_graph_index(mgn_graph* g, const int32_t* d_senders, const int32_t*
   cudaFree(counts);
   cudaFree(inv_perm);
   cudaFree(flags);
+
+  // Node-aligned edge tiles (host greedy packing of whole CSR segments into <= 128 rows / nodes).
+  {
+    std::vector<int32_t> rp((size_t)N + 1);
+    MGN_CUDA_TRY(cudaMemcpy(rp.data(), g->row_ptr, sizeof(int32_t) * (N + 1), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> trow{0}, tnode{0};
+    bool ok = true;
+    int rows = 0, nodes = 0;
+    for (int64_t v = 0; v < N; ++v) {
+      const int deg = rp[v + 1] - rp[v];
+      if (deg > 128) ok = false;
+      if (rows + deg > 128 || nodes == 128) {
+        trow.push_back(rp[v]);
+        tnode.push_back((int32_t)v);
+        rows = 0;
+        nodes = 0;
+      }
+      rows += deg;
+      ++nodes;
+    }
+    trow.push_back(rp[N]);
+    tnode.push_back((int32_t)N);
+    g->tiles_ok = ok;
+    g->n_edge_tiles = (int32_t)trow.size() - 1;
+    MGN_CUDA_TRY(cudaMalloc(&g->tile_row_start, sizeof(int32_t) * trow.size()));
+    MGN_CUDA_TRY(cudaMalloc(&g->tile_node_start, sizeof(int32_t) * tnode.size()));
+    MGN_CUDA_TRY(cudaMemcpy(g->tile_row_start, trow.data(), sizeof(int32_t) * trow.size(), cudaMemcpyHostToDevice));
+    MGN_CUDA_TRY(cudaMemcpy(g->tile_node_start, tnode.data(), sizeof(int32_t) * tnode.size(), cudaMemcpyHostToDevice));
+  }
   return MGN_OK;
 }
 

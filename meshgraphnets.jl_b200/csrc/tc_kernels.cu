@@ -1,0 +1,433 @@
+// tcgen05 kernels of the Encode-Process-Decode path (MGN_COMPUTE_BF16), sm_100a only.
+//
+// mlp_fwd_kernel: one launch runs a whole GraphNetCore MLP (Dense x L -> LayerNorm -> residual ->
+// segmented aggregation) for every 128-row tile it owns.  Per tile:
+//   * the producer warp stages the layer-0 operand (gathered sender / receiver node latents and the
+//     edge latent) as 128B-swizzled K-major tiles with 16-byte cp.async, and streams
+//     the pre-swizzled bf16 weight images with 1-D bulk (TMA) copies through a 4-slot ring;
+//   * one thread of the MMA warp issues tcgen05.mma (M=128, N=128, K=16) into a 128-column fp32
+//     TMEM accumulator;
+//   * four epilogue warps (thread == row) read TMEM, add bias, apply ReLU and write the next
+//     layer's A operand straight back into shared memory as bf16 - hidden activations never leave
+//     the SM; the last layer's epilogue does LayerNorm, the residual add and the deterministic
+//     CSR segmented sum (a11) from shared memory, so the per-edge message never touches HBM.
+// Two CTAs are resident per SM (<= 113 KB smem, 128 TMEM columns each) so one CTA's epilogue
+// overlaps the other's MMAs.
+#include "tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace mgn {
+namespace tc {
+namespace {
+
+constexpr int kRing = 4;
+constexpr int kThreads = 192;  // warps 0-3: epilogue, warp 4: producer, warp 5: MMA issue
+constexpr uint32_t kSmemRing = 0;
+constexpr uint32_t kSmemH = kRing * kTileB;                  // 2 tiles: hidden activation / xhat
+constexpr uint32_t kSmemBias = kSmemH + 2 * kTileB;          // [kMaxLayers][128] fp32
+constexpr uint32_t kSmemLn = kSmemBias + kMaxLayers * 512;   // scale[128], bias[128]
+constexpr uint32_t kSmemBar = kSmemLn + 1024;                // full[4], empty[4], acc_full, epi_done
+constexpr uint32_t kSmemTmem = kSmemBar + 16 * 8;
+constexpr uint32_t kSmemTotal = kSmemTmem + 16;
+constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;          // slack for the 1024 B alignment
+
+// ---------------------------------------------------------------------------------------------------
+// Weight packing: fp32 Julia-layout weights -> bf16 128B-swizzled K-major image tiles.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+pack_kernel(const PackTile* __restrict__ tiles, const float* __restrict__ params,
+            __nv_bfloat16* __restrict__ images) {
+  const PackTile t = tiles[blockIdx.x];
+  const float* W = params + t.w_off;  // [in][out] row-major
+  uint8_t* dst = reinterpret_cast<uint8_t*>(images) + (size_t)blockIdx.x * kTileB;
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    int n, c;
+    if (t.kind == 0) {  // n fastest: W[k][n] is contiguous in n
+      n = i & 127;
+      c = i >> 7;
+    } else {            // chunk fastest: W[n][k] is contiguous in k
+      c = i & 7;
+      n = i >> 3;
+    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = t.kb * 64 + c * 8 + j;
+      if (t.kind == 0) {
+        v[j] = (k < t.in_dim && n < t.out_dim) ? W[(int64_t)k * t.out_dim + n] : 0.f;
+      } else {
+        const int row = t.nb * 128 + n;
+        v[j] = (row < t.in_dim && k < t.out_dim) ? W[(int64_t)row * t.out_dim + k] : 0.f;
+      }
+    }
+    uint4 q;
+    q.x = pack_bf16x2(v[0], v[1]);
+    q.y = pack_bf16x2(v[2], v[3]);
+    q.z = pack_bf16x2(v[4], v[5]);
+    q.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(dst + t128_off(n, c)) = q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fused MLP forward
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_rows(const FwdParams& p, int tile, int64_t& row0, int& cnt) {
+  if (p.tile_row_start) {
+    row0 = p.tile_row_start[tile];
+    cnt = p.tile_row_start[tile + 1] - (int)row0;
+  } else {
+    row0 = (int64_t)tile * kTile;
+    cnt = (int)min((int64_t)kTile, p.M - row0);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t s_ring = s_base + kSmemRing, s_h = s_base + kSmemH;
+  float* bias_s = reinterpret_cast<float*>(smem + kSmemBias);
+  float* ln_s = reinterpret_cast<float*>(smem + kSmemLn);
+  const uint32_t bar0 = s_base + kSmemBar;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kRing), epi_done = bar0 + 8u * (2 * kRing + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemTmem);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = p.n_layers;
+
+  // ---- one-time setup
+  for (int i = tid; i < L * 128; i += kThreads) {
+    const int l = i >> 7, c = i & 127;
+    const int nout = (l == L - 1) ? p.n_out_last : 128;
+    bias_s[i] = c < nout ? p.bias[l][c] : 0.f;
+  }
+  if (p.fin_mode != FIN_LINEAR)
+    for (int i = tid; i < 256; i += kThreads) ln_s[i] = i < 128 ? p.ln_scale[i] : p.ln_bias[i - 128];
+  if (tid == 0) {
+    for (int s = 0; s < kRing; ++s) {
+      mbar_init(full_bar(s), 32);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(epi_done, 128);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================ producer ================================
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int64_t row0;
+      int cnt;
+      tile_rows(p, tile, row0, cnt);
+      for (int l = 0; l < L; ++l) {
+        for (int kb = 0; kb < p.nkb[l]; ++kb) {
+          if (l == 0) {
+            // ---- A tile kb of the layer-0 operand
+            const int s = it % kRing;
+            mbar_wait(empty_bar(s), ((it / kRing) & 1) ^ 1);
+            const uint32_t dst = s_ring + s * kTileB;
+            if (p.in_mode == IN_RAW) {
+#pragma unroll 1
+              for (int rr = 0; rr < 4; ++rr) {
+                const int r = lane + 32 * rr;
+                const bool ok = r < cnt;
+                const int64_t src_row = ok ? (p.raw_idx ? (int64_t)p.raw_idx[row0 + r] : row0 + r) : 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  float v[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const int f = kb * 64 + c * 8 + j;
+                    v[j] = (ok && f < p.raw_F) ? p.raw[src_row * p.raw_F + f] : 0.f;
+                  }
+                  st_shared_v4(dst + t128_off(r, c), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                               pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                }
+              }
+              fence_proxy_async();
+              mbar_arrive(full_bar(s));
+            } else {
+              const __nv_bfloat16* src_base;
+              const int32_t* idx = nullptr;
+              const int seg = kb >> 1;
+              if (p.in_mode == IN_GATHER3) {
+                src_base = seg == 2 ? p.x2 : p.x0;
+                idx = seg == 0 ? p.idx0 : (seg == 1 ? p.idx1 : nullptr);
+              } else {
+                src_base = seg == 0 ? p.x0 : p.x1;
+              }
+#pragma unroll 1
+              for (int rr = 0; rr < 4; ++rr) {
+                const int r = lane + 32 * rr;
+                const bool ok = r < cnt;
+                const int64_t src_row = ok ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + src_row * 128 + (kb & 1) * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) cp_async16(dst + t128_off(r, c), src + c * 16, ok ? 16u : 0u);
+              }
+              cp_async_arrive_noinc(full_bar(s));
+            }
+            ++it;
+          }
+          // ---- weight tile (l, kb)
+          const int s = it % kRing;
+          mbar_wait(empty_bar(s), ((it / kRing) & 1) ^ 1);
+          if (lane == 0) {
+            const uint32_t bytes = (l == L - 1 && p.fin_mode == FIN_LINEAR) ? 16u * 128u : (uint32_t)kTileB;
+            mbar_arrive_expect_tx(full_bar(s), bytes);
+            bulk_g2s(s_ring + s * kTileB, reinterpret_cast<const uint8_t*>(p.wimg[l]) + (size_t)kb * kTileB, bytes,
+                     full_bar(s));
+          } else {
+            mbar_arrive(full_bar(s));
+          }
+          ++it;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issue ================================
+    if (lane == 0) {
+      uint32_t it = 0, epi_par = 0;
+      bool first = true;
+      const uint32_t idesc_full = umma_idesc(128, 128, false, false);
+      const uint32_t idesc_last = p.fin_mode == FIN_LINEAR ? umma_idesc(128, 16, false, false) : idesc_full;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < L; ++l) {
+          if (!first) {  // TMEM drained and (l > 0) the next A operand written by the epilogue
+            mbar_wait(epi_done, epi_par);
+            epi_par ^= 1;
+          }
+          first = false;
+          tc_fence_after();
+          const uint32_t idesc = l == L - 1 ? idesc_last : idesc_full;
+          const int ksteps = l == 0 ? p.ksteps0 : 4;
+          for (int kb = 0; kb < p.nkb[l]; ++kb) {
+            int sa = -1;
+            if (l == 0) {
+              sa = it % kRing;
+              mbar_wait(full_bar(sa), (it / kRing) & 1);
+              ++it;
+            }
+            const int sw = it % kRing;
+            mbar_wait(full_bar(sw), (it / kRing) & 1);
+            ++it;
+            fence_proxy_async();
+            tc_fence_after();
+            const uint32_t a_tile = l == 0 ? s_ring + sa * kTileB : s_h + kb * kTileB;
+            const uint32_t b_tile = s_ring + sw * kTileB;
+            for (int k = 0; k < ksteps; ++k)
+              umma(tmem, desc_kmajor(a_tile, k), desc_kmajor(b_tile, k), idesc, (kb | k) != 0);
+            umma_commit(empty_bar(sw));
+            if (l == 0) umma_commit(empty_bar(sa));
+          }
+          umma_commit(acc_full);
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (thread == row) ================================
+    uint32_t acc_par = 0;
+    bool store_pending = false;
+    const int row = tid;  // 0..127
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int64_t row0;
+      int cnt;
+      tile_rows(p, tile, row0, cnt);
+      for (int l = 0; l < L; ++l) {
+        mbar_wait(acc_full, acc_par);
+        acc_par ^= 1;
+        tc_fence_after();
+        const bool last = l == L - 1;
+        if (last && p.fin_mode == FIN_LINEAR) {
+          float v[16];
+          tmem_ld16(t_lane, v);
+          tc_fence_before();
+          mbar_arrive(epi_done);
+          if (row < cnt)
+            for (int j = 0; j < p.out_dim; ++j) p.out[(row0 + row) * p.out_dim + j] = v[j] + bias_s[l * 128 + j];
+          continue;
+        }
+        // the shared activation tile is about to be overwritten: every thread must be done reading the
+        // previous tile's copy-out / aggregation, and a pending bulk store must have read it
+        if (tid == 0 && store_pending) {
+          bulk_wait_read0();
+          store_pending = false;
+        }
+        named_bar_sync(1, 128);
+        float mean = 0.f, rstd = 1.f;
+        if (last) {  // LayerNorm statistics: two extra passes over TMEM (cheap), biased variance
+          float s = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tmem_ld32(t_lane + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s += v[j] + bias_s[l * 128 + c * 32 + j];
+          }
+          mean = s * (1.f / 128.f);
+          float q = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tmem_ld32(t_lane + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float d = v[j] + bias_s[l * 128 + c * 32 + j] - mean;
+              q = fmaf(d, d, q);
+            }
+          }
+          rstd = 1.f / sqrtf(q * (1.f / 128.f) + p.eps);
+          if (p.save_rstd && row < cnt) p.save_rstd[row0 + row] = rstd;
+        }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = v[2 * j] + bias_s[l * 128 + c * 32 + 2 * j];
+            float b = v[2 * j + 1] + bias_s[l * 128 + c * 32 + 2 * j + 1];
+            if (last) {
+              a = (a - mean) * rstd;
+              b = (b - mean) * rstd;
+            } else {
+              a = fmaxf(a, 0.f);
+              b = fmaxf(b, 0.f);
+            }
+            w[j] = pack_bf16x2(a, b);
+          }
+          const uint32_t tb = s_h + (c >> 1) * kTileB;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            st_shared_v4(tb + t128_off(row, (c & 1) * 4 + q4), w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __nv_bfloat16* save = last ? p.save_xhat : p.save_h[l];
+        if (!last) {
+          if (save) {
+            named_bar_sync(1, 128);
+            if (tid == 0) {
+              bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
+              bulk_commit();
+              store_pending = true;
+            }
+          }
+          mbar_arrive(epi_done);
+          continue;
+        }
+        // ---- last layer: TMEM is drained -> the MMA warp may start the next tile
+        mbar_arrive(epi_done);
+        named_bar_sync(1, 128);
+        if (save && tid == 0) {
+          bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
+          bulk_commit();
+          store_pending = true;
+        }
+        // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced)
+        {
+          const int cc = tid & 15, rg = tid >> 4;
+          float sc[8], bi[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            sc[j] = ln_s[cc * 8 + j];
+            bi[j] = ln_s[128 + cc * 8 + j];
+          }
+#pragma unroll 1
+          for (int i = rg; i < cnt; i += 8) {
+            const uint4 xq = ld_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7));
+            const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+            float m[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
+              m[2 * j] = fmaf(__low2float(h), sc[2 * j], bi[2 * j]);
+              m[2 * j + 1] = fmaf(__high2float(h), sc[2 * j + 1], bi[2 * j + 1]);
+            }
+            const int64_t o = (row0 + i) * 128 + cc * 8;
+            if (p.fin_mode != FIN_LN) {
+              const float4 r0 = *reinterpret_cast<const float4*>(p.lat_in + o);
+              const float4 r1 = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+              m[0] += r0.x; m[1] += r0.y; m[2] += r0.z; m[3] += r0.w;
+              m[4] += r1.x; m[5] += r1.y; m[6] += r1.z; m[7] += r1.w;
+            }
+            *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4*>(p.lat_out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+            uint4 bq;
+            bq.x = pack_bf16x2(m[0], m[1]);
+            bq.y = pack_bf16x2(m[2], m[3]);
+            bq.z = pack_bf16x2(m[4], m[5]);
+            bq.w = pack_bf16x2(m[6], m[7]);
+            *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
+          }
+        }
+        // ---- deterministic segmented sum of the (pre-residual) messages: thread == column, rows in
+        //      ascending CSR slot = ascending original edge id (the CPU scatter order, a11)
+        if (p.fin_mode == FIN_LN_RESID_AGG) {
+          const int col = tid;
+          const float sc = ln_s[col], bi = ln_s[128 + col];
+          const uint32_t cbase = s_h + (col >> 6) * kTileB + (col & 7) * 2;
+          const int chunk = (col & 63) >> 3;
+          const int n0 = p.tile_node_start[tile], n1 = p.tile_node_start[tile + 1];
+          int jb = p.row_ptr[n0] - (int)row0;
+          for (int v = n0; v < n1; ++v) {
+            const int je = p.row_ptr[v + 1] - (int)row0;
+            float acc = 0.f;
+            for (int j = jb; j < je; ++j) {
+              uint16_t hx;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(cbase + t128_off(j, chunk)));
+              acc += fmaf(__bfloat162float(__ushort_as_bfloat16(hx)), sc, bi);
+            }
+            p.agg_bf16[(int64_t)v * 128 + col] = __float2bfloat16_rn(acc);
+            jb = je;
+          }
+        }
+      }
+    }
+    if (tid == 0 && store_pending) bulk_wait0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 128);
+}
+
+}  // namespace
+
+cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat16* images, cudaStream_t st) {
+  if (im.n_tiles == 0) return cudaSuccess;
+  ProfScope ps(TAG_TC_PACK, st);
+  pack_kernel<<<im.n_tiles, 256, 0, st>>>(im.d_tiles, params, images);
+  return cudaGetLastError();
+}
+
+cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
+  if (p.n_tiles == 0) return cudaSuccess;
+  static bool configured = false;
+  static int n_sm = 148;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLaunch);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  const int grid = p.n_tiles < 2 * n_sm ? p.n_tiles : 2 * n_sm;
+  ProfScope ps(TAG_TC_MLP_FWD, st);
+  mlp_fwd_kernel<<<grid, kThreads, kSmemLaunch, st>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace mgn

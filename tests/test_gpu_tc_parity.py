@@ -1,0 +1,97 @@
+"""Tensor-core mode (MGN_COMPUTE_BF16: bf16 operands, fp32 accumulation in TMEM, fp32 master latents)
+against the fp64 CPU oracle, through the C ABI.  Tolerances are the bf16-mode tolerances stated in
+DESIGN.md: 3e-2 relative L2 on outputs after the residual stack, 6e-2 on gradients."""
+import numpy as np
+import pytest
+import torch
+
+import mgn_oracle as orc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+
+TOL_OUT = 3e-2
+TOL_GRAD = 6e-2
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _problem(nx, ny, mps, node_in=9, edge_in=3, seed=0, hidden=2):
+    rng = np.random.default_rng(seed)
+    pos, cells, nt = orc.cylinder_flow_mesh(nx, ny)
+    s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
+    N, E = pos.shape[0], s.shape[0]
+    cfg = orc.ModelConfig(node_in, edge_in, 2, 128, mps, hidden)
+    ps = (orc.init_params(cfg, seed=seed + 1, dtype=np.float64)
+          + 0.02 * rng.normal(size=orc.mlp_specs(cfg)[1])).astype(np.float32)
+    nf = rng.normal(size=(N, node_in)).astype(np.float32)
+    ef = rng.normal(size=(E, edge_in)).astype(np.float32)
+    tgt = rng.normal(size=(N, 2)).astype(np.float32)
+    mask = orc.node_mask(nt, [0, 5])
+    return cfg, ps, nf, ef, s, r, tgt, mask
+
+
+@pytest.mark.parametrize("nx,ny,mps,hidden", [(5, 4, 1, 2), (12, 9, 3, 2), (30, 17, 2, 1), (9, 6, 2, 0)])
+def test_forward_bf16_matches_oracle(pkg, nx, ny, mps, hidden):
+    cfg, ps, nf, ef, s, r, tgt, mask = _problem(nx, ny, mps, hidden=hidden)
+    out_o = orc.model_forward(cfg, ps.astype(np.float64), nf, ef, s, r, dtype=np.float64)
+    model = pkg.Model(9, 3, 2, mps, 128, hidden, compute_mode=pkg.COMPUTE_BF16)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    a = model.forward(graph, dev(ps), training=False)
+    b = model.forward(graph, dev(ps), training=True)
+    torch.cuda.synchronize()
+    assert rel(a.cpu().numpy(), out_o) < TOL_OUT
+    assert torch.equal(a, b)                       # inference and training forwards are the same arithmetic
+    assert torch.equal(a, model.forward(graph, dev(ps), training=False))   # deterministic (no atomics)
+
+
+def test_forward_bf16_full_size(pkg):
+    """BASELINE configs[1] at full size: N=1885, E=10936, 15 MP steps."""
+    cfg, ps, nf, ef, s, r, tgt, mask = _problem(65, 29, 15)
+    out_o = orc.model_forward(cfg, ps, nf, ef, s, r, dtype=np.float32)
+    model = pkg.Model(9, 3, 2, 15, 128, 2, compute_mode=pkg.COMPUTE_BF16)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    a = model.forward(graph, dev(ps), training=False)
+    assert rel(a.cpu().numpy(), out_o) < TOL_OUT
+
+
+def test_bf16_agrees_with_fp32_mode_on_device(pkg):
+    """Property at a size the oracle does not reach in seconds: the two compute modes of the library
+    agree within the bf16 tolerance on a 60k-edge mesh."""
+    cfg, ps, nf, ef, s, r, tgt, mask = _problem(120, 85, 4)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    m32 = pkg.Model(9, 3, 2, 4, 128, 2, compute_mode=pkg.COMPUTE_FP32)
+    m16 = pkg.Model(9, 3, 2, 4, 128, 2, compute_mode=pkg.COMPUTE_BF16)
+    a = m32.forward(graph, dev(ps))
+    b = m16.forward(graph, dev(ps))
+    assert rel(b.cpu().numpy(), a.cpu().numpy()) < TOL_OUT
+
+
+def test_step_bf16_matches_oracle(pkg):
+    cfg, ps, nf, ef, s, r, tgt, mask = _problem(12, 9, 3)
+    g_o, loss_o, out_o, dnf_o = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
+    model = pkg.Model(9, 3, 2, 3, 128, 2, compute_mode=pkg.COMPUTE_BF16)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
+    try:
+        (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
+    except pkg.MgnError as e:
+        if e.code == 5:
+            pytest.skip("bf16 backward not built yet")
+        raise
+    assert abs(float(loss.cpu()) - loss_o) < TOL_OUT * abs(loss_o)
+    assert rel(gs.cpu().numpy(), g_o) < TOL_GRAD
+    for name, off, rows, cols in model.param_layout():
+        ref = g_o[off:off + rows * cols]
+        got = gs[off:off + rows * cols].cpu().numpy()
+        assert np.linalg.norm(got - ref) <= 0.15 * np.linalg.norm(ref) + 1e-3 * np.linalg.norm(g_o), name
+    out = model.forward(graph, dev(ps), training=True)
+    _, dout_o = orc.loss_and_dout(out_o, tgt.astype(np.float64), mask)
+    dps, dnf = model.backward(graph, dev(ps), dev(dout_o.astype(np.float32)), want_dnf=True)
+    assert rel(dnf.cpu().numpy(), dnf_o) < TOL_GRAD
