@@ -95,5 +95,80 @@ struct FwdParams {
 
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st);
 
+// ---- fused MLP backward ----------------------------------------------------------------------------
+// Chain kernel: LayerNorm backward (or a precomputed top-level dZ image) followed by `nsteps` steps;
+// step j handles Dense layer l = top - j:   dW_l += H_{l-1}^T dZ_l  (accumulated in TMEM over all tiles
+// of the CTA),  dZ_{l-1} = (dZ_l W_l^T) .* (H_{l-1} > 0),  db = column sums of every dZ.  The last dZ
+// (dZ of layer top - nsteps) is written as a tile image for the input kernel.
+enum HeadMode { HEAD_LN = 0, HEAD_IMAGE = 1 };
+constexpr int kMaxSteps = kMaxLayers - 1;
+
+struct ChainParams {
+  int n_tiles;
+  int64_t M;
+  const int32_t* tile_row_start;       // nullable (plain 128-row tiles)
+  int head_mode;
+  // HEAD_LN: dy[r] = dy_a[r] + dy_b[b_idx ? b_idx[r] : r]   (either may be null)
+  const float* dy_a;
+  const float* dy_b;
+  const int32_t* b_idx;
+  const __nv_bfloat16* xhat;           // image
+  const float* rstd;                   // [rows]
+  const float* ln_scale;               // [128]
+  // HEAD_IMAGE
+  const __nv_bfloat16* z_top;          // image
+  int nsteps;                          // 1..kMaxSteps
+  const __nv_bfloat16* h_img[kMaxSteps];   // step j: H_{l-1} image
+  const __nv_bfloat16* wt_img[kMaxSteps];  // step j: W_l^T image (2 tiles)
+  __nv_bfloat16* dz_out;               // image of the last dZ
+  float* partial;                      // [grid][chain_partial_floats(nsteps)]
+};
+// per-CTA partial layout: dW[j] at j*16384 ; db[i] at nsteps*16384 + i*128 (i = 0: top dZ, i = j+1: dZ
+// produced by step j) ; g_scale, g_bias after the db block.
+__host__ __device__ inline size_t chain_partial_floats(int nsteps) { return (size_t)nsteps * 16384 + (size_t)(nsteps + 1) * 128 + 256; }
+int backward_grid(int n_tiles);   // CTAs a backward kernel launches for n_tiles tiles
+cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStream_t st);
+
+// Input kernel: first Dense layer of an MLP whose input is made of 128-wide bf16 blocks.
+//   dW_0[block b] += X_b^T dZ_0 ; dX_b = dZ_0 W_0[block b]^T -> sink b
+enum SinkMode { SINK_NONE = 0, SINK_STORE_BF16 = 1, SINK_ADD_F32 = 2, SINK_SEGSUM_F32 = 3 };
+struct InputParams {
+  int n_tiles;
+  int64_t M;
+  const int32_t* tile_row_start;
+  const int32_t* tile_node_start;      // SINK_SEGSUM_F32
+  const int32_t* row_ptr;
+  const __nv_bfloat16* dz0;            // image
+  int nblk;                            // 1..3
+  const __nv_bfloat16* x[3];           // block b source, row-major [*][128]
+  const int32_t* idx[3];               // optional row gather
+  const __nv_bfloat16* wt_img;         // W_0^T image: tile (nb, kb) at (nb * 2 + kb) * 16 KB
+  int sink[3];
+  float* f32_dst[3];                   // SINK_ADD_F32: dst[r] = (src ? src[r] : 0) + dX ; SINK_SEGSUM_F32: per node
+  const float* f32_src[3];
+  __nv_bfloat16* bf16_dst[3];
+  float* partial;                      // [grid][nblk * 16384]
+};
+cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st);
+
+// ---- small CUDA-core helpers of the backward pass ---------------------------------------------------
+struct Piece { int64_t src_off; float* dst; int64_t count; };
+constexpr int kMaxPieces = 12;
+struct Pieces { Piece p[kMaxPieces]; int n; };
+// dst[i] = sum_k partial[k * stride + src_off + i]   (fixed order: deterministic)
+cudaError_t reduce_pieces(const float* partial, int n_parts, int64_t stride, const Pieces& pieces, cudaStream_t st);
+// Decoder head: dZ_{L-2} = (dout W_{L-1}^T) .* (H_{L-2} > 0) as an image, plus per-tile partials of
+// dW_{L-1} [128][od], db_{L-1} [od] and db_{L-2} [128]  (stride 128*od + od + 128 floats per tile).
+cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,
+                             int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, cudaStream_t st);
+// Encoder input layer: dW_0 [F][128] per-tile partials from the dZ_0 image and the raw fp32 features;
+// d_raw [rows][F] = dZ_0 W_0^T when requested.
+cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const int32_t* raw_idx, int F,
+                              const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
+                              float* partial, float* d_raw, cudaStream_t st);
+// d_nf[v] += sum over CSC row v of dxs[csc_slot[j]]  (adjoint of the sender gather, deterministic)
+cudaError_t sender_gather_add(float* d_nf, const __nv_bfloat16* dxs, const int32_t* col_ptr,
+                              const int32_t* csc_slot, int64_t N, cudaStream_t st);
+
 }  // namespace tc
 }  // namespace mgn

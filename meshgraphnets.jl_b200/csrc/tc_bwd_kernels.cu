@@ -1,0 +1,874 @@
+// tcgen05 kernels of the backward pass (MGN_COMPUTE_BF16), sm_100a only.
+//
+// mlp_bwd_chain_kernel   one launch = the Dense layers top .. 1 of one GraphNetCore MLP, for every 128-row
+//                        tile the CTA owns.  Per tile: the head warps do the LayerNorm backward straight from
+//                        the fp32 gradient of the MLP output (gathering the aggregation adjoint d_agg[recv],
+//                        SURVEY 8 a11) and write dZ_top as a 128B-swizzled bf16 operand tile; then for each
+//                        layer one MMA thread issues  dX = dZ W^T  (K-major operands) into a TMEM
+//                        accumulator and  dW += H^T dZ  (the SAME shared-memory bytes read as MN-major
+//                        operands) into per-layer TMEM accumulators that live across all tiles of the CTA -
+//                        weight gradients are reduced on chip and leave the SM once per launch.  The
+//                        epilogue warps apply the ReLU mask and write the next dZ tile back to shared memory;
+//                        hidden gradients never touch HBM.
+// mlp_bwd_input_kernel   first Dense layer: dW_0 += X^T dZ_0 with X gathered exactly like the forward operand
+//                        (sender rows, receiver rows, edge latent) and dX = dZ_0 W_0^T scattered by fused sinks:
+//                        bf16 rows for the sender adjoint, a deterministic CSR segmented sum for the receiver
+//                        adjoint, an in-place fp32 add for the edge-latent gradient.
+// Cross-CTA reduction of the weight-gradient partials is a fixed-order sum (reduce_pieces): deterministic.
+#include "tc.cuh"
+#include "tc_ptx.cuh"
+
+namespace mgn {
+namespace tc {
+namespace {
+
+constexpr uint32_t kImg = 2 * kTileB;  // one 128 x 128 bf16 operand (two T128 tiles)
+
+__device__ __forceinline__ void tile_rows(const int32_t* trs, int64_t M, int tile, int64_t& row0, int& cnt) {
+  if (trs) {
+    row0 = trs[tile];
+    cnt = trs[tile + 1] - (int)row0;
+  } else {
+    row0 = (int64_t)tile * kTile;
+    cnt = (int)min((int64_t)kTile, M - row0);
+  }
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
+
+// ======================================================================================================
+// Chain kernel
+// ======================================================================================================
+namespace chain {
+constexpr int kThreads = 320;  // warps 0-3 epilogue, 4-7 head (LayerNorm backward), 8 producer, 9 MMA
+constexpr int kZ = 3, kH = 2, kW = 3;
+constexpr uint32_t kSmemZ = 0;
+constexpr uint32_t kSmemH = kSmemZ + kZ * kImg;
+constexpr uint32_t kSmemW = kSmemH + kH * kImg;
+constexpr uint32_t kSmemScale = kSmemW + kW * kTileB;         // ln scale [128]
+constexpr uint32_t kSmemRed = kSmemScale + 512;               // [8][3][128] fp32
+constexpr uint32_t kSmemBar = kSmemRed + 8 * 3 * 128 * 4;
+constexpr uint32_t kNumBar = 2 * kZ + 2 * kH + 2 * kW + 4;
+constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
+constexpr uint32_t kSmemTotal = kSmemTmem + 16;
+constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  float* scale_s = reinterpret_cast<float*>(smem + kSmemScale);
+  float* red_s = reinterpret_cast<float*>(smem + kSmemRed);
+  const uint32_t bar0 = s_base + kSmemBar;
+  auto z_full = [&](int s) { return bar0 + 8u * s; };
+  auto z_empty = [&](int s) { return bar0 + 8u * (kZ + s); };
+  auto h_full = [&](int s) { return bar0 + 8u * (2 * kZ + s); };
+  auto h_empty = [&](int s) { return bar0 + 8u * (2 * kZ + kH + s); };
+  auto w_full = [&](int s) { return bar0 + 8u * (2 * kZ + 2 * kH + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (2 * kZ + 2 * kH + kW + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kZ + 2 * kH + 2 * kW);
+  const uint32_t acc_empty = acc_full + 8, done_bar = acc_full + 16;
+  // head_go: phase t completes when the MMAs of step 0 of the CTA's t-th tile are done.  The writer of the next
+  // tile's top dZ waits for it, so it never runs more than one use ahead of a Z slot's parity.
+  const uint32_t head_go = acc_full + 24;
+  auto z_slot = [&](int s) { return s_base + kSmemZ + (uint32_t)s * kImg; };
+  auto h_slot = [&](int s) { return s_base + kSmemH + (uint32_t)s * kImg; };
+  auto w_slot = [&](int s) { return s_base + kSmemW + (uint32_t)s * (uint32_t)kTileB; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemTmem);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ns = p.nsteps;
+  float* my_partial = p.partial + (size_t)blockIdx.x * chain_partial_floats(ns);
+
+  if (p.head_mode == HEAD_LN)
+    for (int i = tid; i < 128; i += kThreads) scale_s[i] = p.ln_scale[i];
+  if (tid == 0) {
+    for (int s = 0; s < kZ; ++s) {
+      mbar_init(z_full(s), 1);
+      mbar_init(z_empty(s), 2);
+    }
+    for (int s = 0; s < kH; ++s) {
+      mbar_init(h_full(s), 1);
+      mbar_init(h_empty(s), 2);
+    }
+    for (int s = 0; s < kW; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    mbar_init(done_bar, 1);
+    mbar_init(head_go, 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 8) {
+    // ================================ producer (one thread: bulk copies only) ========================
+    if (lane == 0) {
+      uint32_t hc = 0, wc = 0, t_local = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+        if (p.head_mode == HEAD_IMAGE) {
+          const uint32_t zc = t_local * (ns + 1), s = zc % kZ;
+          if (t_local > 0) mbar_wait(head_go, (t_local - 1) & 1);
+          mbar_wait(z_empty(s), ((zc / kZ) & 1) ^ 1);
+          mbar_arrive_expect_tx(z_full(s), kImg);
+          bulk_g2s(z_slot(s), reinterpret_cast<const uint8_t*>(p.z_top) + (size_t)tile * kImg, kImg, z_full(s));
+          mbar_arrive(z_empty(s));  // stands in for the head warps' "column sums done" arrival
+        }
+        for (int j = 0; j < ns; ++j) {
+          for (int kb = 0; kb < 2; ++kb, ++wc) {
+            const uint32_t s = wc % kW;
+            mbar_wait(w_empty(s), ((wc / kW) & 1) ^ 1);
+            mbar_arrive_expect_tx(w_full(s), (uint32_t)kTileB);
+            bulk_g2s(w_slot(s), reinterpret_cast<const uint8_t*>(p.wt_img[j]) + (size_t)kb * kTileB, (uint32_t)kTileB,
+                     w_full(s));
+          }
+          const uint32_t s = hc % kH;
+          mbar_wait(h_empty(s), ((hc / kH) & 1) ^ 1);
+          mbar_arrive_expect_tx(h_full(s), kImg);
+          bulk_g2s(h_slot(s), reinterpret_cast<const uint8_t*>(p.h_img[j]) + (size_t)tile * kImg, kImg, h_full(s));
+          ++hc;
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ================================ MMA issue ================================
+    if (lane == 0) {
+      const uint32_t idesc_k = umma_idesc(128, 128, false, false);
+      const uint32_t idesc_mn = umma_idesc(128, 128, true, true);
+      uint32_t hc = 0, wc = 0, t_local = 0, acc_par = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+        for (int j = 0; j < ns; ++j) {
+          const uint32_t zc = t_local * (ns + 1) + j, zs = zc % kZ;
+          mbar_wait(z_full(zs), (zc / kZ) & 1);
+          if (!first) {  // the epilogue has drained the accumulator of the previous step
+            mbar_wait(acc_empty, acc_par);
+            acc_par ^= 1;
+          }
+          first = false;
+          fence_proxy_async();
+          tc_fence_after();
+          // dX = dZ W^T : A = dZ (K-major over the layer's output features), B = W^T image tile kb
+          for (int kb = 0; kb < 2; ++kb, ++wc) {
+            const uint32_t ws = wc % kW;
+            mbar_wait(w_full(ws), (wc / kW) & 1);
+            tc_fence_after();
+            for (int k = 0; k < 4; ++k)
+              umma(tmem, desc_kmajor(z_slot(zs) + kb * kTileB, k), desc_kmajor(w_slot(ws), k), idesc_k, (kb | k) != 0);
+            umma_commit(w_empty(ws));
+          }
+          umma_commit(acc_full);
+          // dW += H^T dZ : both operands read MN-major (rows of the tile are the reduction index)
+          const uint32_t hs = hc % kH;
+          mbar_wait(h_full(hs), (hc / kH) & 1);
+          tc_fence_after();
+          const uint32_t d_w = tmem + 128u * (1 + j);
+          for (int ks = 0; ks < 8; ++ks)
+            umma(d_w, desc_mnmajor(h_slot(hs), (uint32_t)kTileB, ks), desc_mnmajor(z_slot(zs), (uint32_t)kTileB, ks),
+                 idesc_mn, (t_local | ks) != 0);
+          umma_commit(h_empty(hs));
+          umma_commit(z_empty(zs));
+          if (j == 0) umma_commit(head_go);
+          ++hc;
+        }
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp < 4) {
+    // ================================ epilogue (thread == row) ================================
+    const int row = tid;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t hc = 0, t_local = 0, acc_par = 0;
+    float db[kMaxSteps] = {0.f, 0.f, 0.f};
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+      int64_t row0;
+      int cnt;
+      tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
+#pragma unroll 1
+      for (int j = 0; j < ns; ++j) {
+        const uint32_t zc = t_local * (ns + 1) + j + 1, zs = zc % kZ, hs = hc % kH;
+        mbar_wait(acc_full, acc_par);
+        acc_par ^= 1;
+        mbar_wait(h_full(hs), (hc / kH) & 1);
+        mbar_wait(z_empty(zs), ((zc / kZ) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          const uint32_t hb = h_slot(hs) + (c >> 1) * kTileB, zb = z_slot(zs) + (c >> 1) * kTileB;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const uint32_t off = t128_off(row, (c & 1) * 4 + q4);
+            const uint4 hq = ld_shared_v4(hb + off);
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = (hw[e] & 0x00007fffu) ? v[q4 * 8 + 2 * e] : 0.f;      // ReLU mask: H > 0
+              const float b = (hw[e] & 0x7fff0000u) ? v[q4 * 8 + 2 * e + 1] : 0.f;
+              w[e] = pack_bf16x2(a, b);
+            }
+            st_shared_v4(zb + off, w[0], w[1], w[2], w[3]);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+        named_bar_sync(1, 128);
+        const bool last = j == ns - 1;
+        if (tid == 0) {
+          mbar_arrive(z_full(zs));
+          mbar_arrive(h_empty(hs));
+          if (last) {
+            bulk_s2g(reinterpret_cast<uint8_t*>(p.dz_out) + (size_t)tile * kImg, z_slot(zs), kImg);
+            bulk_commit();
+          }
+        }
+        // bias gradient: column sums of the bf16 dZ just written (thread == column)
+        {
+          const int col = tid;
+          const uint32_t cbase = z_slot(zs) + (col >> 6) * kTileB + (col & 7) * 2;
+          const int chunk = (col & 63) >> 3;
+          float s = 0.f;
+          for (int r = 0; r < cnt; ++r) {
+            uint16_t hx;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(cbase + t128_off(r, chunk)));
+            s += bf16_bits_to_float(hx);
+          }
+          db[j] += s;
+        }
+        named_bar_sync(1, 128);
+        if (tid == 0) {
+          if (last) {
+            bulk_wait_read0();
+            mbar_arrive(z_empty(zs));  // stands in for the MMA commit: nobody multiplies the last dZ here
+          }
+          mbar_arrive(z_empty(zs));
+        }
+        ++hc;
+      }
+    }
+    // ---- weight-gradient partials: TMEM -> global, once per launch
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    for (int j = 0; j < ns; ++j) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(t_lane + 128u * (1 + j) + c * 32, v);
+        float4* dst = reinterpret_cast<float4*>(my_partial + (size_t)j * 16384 + (size_t)row * 128 + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      my_partial[(size_t)ns * 16384 + (size_t)(j + 1) * 128 + tid] = db[j];
+    }
+    if (tid == 0) bulk_wait0();
+  } else {
+    // ================================ head: LayerNorm backward (16 lanes per row) ================================
+    const int lt = tid - 128, cc = lt & 15, rg = lt >> 4;
+    float gs[8], gb[8], dbt[8], sc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gs[e] = gb[e] = dbt[e] = 0.f;
+    if (p.head_mode == HEAD_LN) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sc[e] = scale_s[cc * 8 + e];
+      uint32_t t_local = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+        int64_t row0;
+        int cnt;
+        tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
+        const uint32_t zc = t_local * (ns + 1), zs = zc % kZ;
+        if (t_local > 0) mbar_wait(head_go, (t_local - 1) & 1);
+        mbar_wait(z_empty(zs), ((zc / kZ) & 1) ^ 1);
+        const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
+        const uint32_t zb = z_slot(zs) + (cc >> 3) * kTileB;
+#pragma unroll 2
+        for (int i = rg; i < kTile; i += 8) {
+          const bool ok = i < cnt;
+          float dy[8], xh[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dy[e] = xh[e] = 0.f;
+          float rs = 0.f;
+          if (ok) {
+            const int64_t r = row0 + i;
+            if (p.dy_a) {
+              const float4 a0 = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
+              const float4 a1 = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
+              dy[0] = a0.x; dy[1] = a0.y; dy[2] = a0.z; dy[3] = a0.w;
+              dy[4] = a1.x; dy[5] = a1.y; dy[6] = a1.z; dy[7] = a1.w;
+            }
+            if (p.dy_b) {
+              const int64_t br = p.b_idx ? (int64_t)p.b_idx[r] : r;
+              const float4 b0 = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8 + 4);
+              dy[0] += b0.x; dy[1] += b0.y; dy[2] += b0.z; dy[3] += b0.w;
+              dy[4] += b1.x; dy[5] += b1.y; dy[6] += b1.z; dy[7] += b1.w;
+            }
+            const uint4 xq = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
+            const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              xh[2 * e] = bf16_bits_to_float(xw[e] & 0xffffu);
+              xh[2 * e + 1] = __uint_as_float(xw[e] & 0xffff0000u);
+            }
+            rs = p.rstd[r];
+          }
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float dxh = dy[e] * sc[e];
+            s1 += dxh;
+            s2 = fmaf(dxh, xh[e], s2);
+            gb[e] += dy[e];
+            gs[e] = fmaf(dy[e], xh[e], gs[e]);
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          const float m1 = s1 * (1.f / 128.f), m2 = s2 * (1.f / 128.f);
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = rs * (dy[2 * e] * sc[2 * e] - m1 - xh[2 * e] * m2);
+            const float b = rs * (dy[2 * e + 1] * sc[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
+            w[e] = pack_bf16x2(a, b);
+            dbt[2 * e] += bf16_bits_to_float(w[e] & 0xffffu);
+            dbt[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+          }
+          st_shared_v4(zb + t128_off(i, cc & 7), w[0], w[1], w[2], w[3]);
+        }
+        fence_proxy_async();
+        named_bar_sync(2, 128);
+        if (lt == 0) {
+          mbar_arrive(z_full(zs));
+          mbar_arrive(z_empty(zs));  // "column sums done": the head warps keep theirs in registers
+        }
+      }
+    }
+    // ---- reduce the per-row-group column sums: [8][3][128] -> [3][128]
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      red_s[(rg * 3 + 0) * 128 + cc * 8 + e] = dbt[e];
+      red_s[(rg * 3 + 1) * 128 + cc * 8 + e] = gs[e];
+      red_s[(rg * 3 + 2) * 128 + cc * 8 + e] = gb[e];
+    }
+    named_bar_sync(2, 128);
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      t0 += red_s[(g * 3 + 0) * 128 + lt];
+      t1 += red_s[(g * 3 + 1) * 128 + lt];
+      t2 += red_s[(g * 3 + 2) * 128 + lt];
+    }
+    float* tail = my_partial + (size_t)ns * 16384;
+    tail[lt] = t0;                                 // db of the top layer
+    tail[(size_t)(ns + 1) * 128 + lt] = t1;        // g_scale
+    tail[(size_t)(ns + 1) * 128 + 128 + lt] = t2;  // g_bias
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem, 512);
+}
+}  // namespace chain
+
+// ======================================================================================================
+// Input kernel
+// ======================================================================================================
+namespace input {
+constexpr int kThreads = 192;  // warps 0-3 epilogue, 4 producer, 5 MMA
+constexpr int kZ = 2, kX = 2, kW = 3;
+constexpr uint32_t kSmemZ = 0;
+constexpr uint32_t kSmemX = kSmemZ + kZ * kImg;
+constexpr uint32_t kSmemW = kSmemX + kX * kImg;
+constexpr uint32_t kSmemStage = kSmemW + kW * kTileB;
+constexpr uint32_t kSmemBar = kSmemStage + kImg;
+constexpr uint32_t kNumBar = 2 * kZ + 2 * kX + 2 * kW + 3;
+constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
+constexpr uint32_t kSmemTotal = kSmemTmem + 16;
+constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + kSmemBar;
+  auto z_full = [&](int s) { return bar0 + 8u * s; };
+  auto z_empty = [&](int s) { return bar0 + 8u * (kZ + s); };
+  auto x_full = [&](int s) { return bar0 + 8u * (2 * kZ + s); };
+  auto x_empty = [&](int s) { return bar0 + 8u * (2 * kZ + kX + s); };
+  auto w_full = [&](int s) { return bar0 + 8u * (2 * kZ + 2 * kX + s); };
+  auto w_empty = [&](int s) { return bar0 + 8u * (2 * kZ + 2 * kX + kW + s); };
+  const uint32_t acc_full = bar0 + 8u * (2 * kZ + 2 * kX + 2 * kW);
+  const uint32_t acc_empty = acc_full + 8, done_bar = acc_full + 16;
+  auto z_slot = [&](int s) { return s_base + kSmemZ + (uint32_t)s * kImg; };
+  auto x_slot = [&](int s) { return s_base + kSmemX + (uint32_t)s * kImg; };
+  auto w_slot = [&](int s) { return s_base + kSmemW + (uint32_t)s * (uint32_t)kTileB; };
+  const uint32_t s_stage = s_base + kSmemStage;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemTmem);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nblk = p.nblk;
+  float* my_partial = p.partial + (size_t)blockIdx.x * (size_t)nblk * 16384;
+
+  if (tid == 0) {
+    for (int s = 0; s < kZ; ++s) {
+      mbar_init(z_full(s), 1);
+      mbar_init(z_empty(s), 1);
+    }
+    for (int s = 0; s < kX; ++s) {
+      mbar_init(x_full(s), 32);
+      mbar_init(x_empty(s), 1);
+    }
+    for (int s = 0; s < kW; ++s) {
+      mbar_init(w_full(s), 1);
+      mbar_init(w_empty(s), 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 128);
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================ producer ================================
+    uint32_t xc = 0, wc = 0, t_local = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+      int64_t row0;
+      int cnt;
+      tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
+      if (lane == 0) {
+        const uint32_t zs = t_local % kZ;
+        mbar_wait(z_empty(zs), ((t_local / kZ) & 1) ^ 1);
+        mbar_arrive_expect_tx(z_full(zs), kImg);
+        bulk_g2s(z_slot(zs), reinterpret_cast<const uint8_t*>(p.dz0) + (size_t)tile * kImg, kImg, z_full(zs));
+      }
+      __syncwarp();
+      for (int b = 0; b < nblk; ++b) {
+        if (lane == 0) {
+          for (int kb = 0; kb < 2; ++kb) {
+            const uint32_t c = wc + kb, s = c % kW;
+            mbar_wait(w_empty(s), ((c / kW) & 1) ^ 1);
+            mbar_arrive_expect_tx(w_full(s), (uint32_t)kTileB);
+            bulk_g2s(w_slot(s), reinterpret_cast<const uint8_t*>(p.wt_img) + (size_t)(b * 2 + kb) * kTileB,
+                     (uint32_t)kTileB, w_full(s));
+          }
+        }
+        wc += 2;
+        __syncwarp();
+        const uint32_t xs = xc % kX;
+        mbar_wait(x_empty(xs), ((xc / kX) & 1) ^ 1);
+        const __nv_bfloat16* src_base = p.x[b];
+        const int32_t* idx = p.idx[b];
+        const uint32_t dst = x_slot(xs);
+#pragma unroll 1
+        for (int rr = 0; rr < 4; ++rr) {
+          const int r = lane + 32 * rr;
+          const bool ok = r < cnt;
+          const int64_t src_row = ok ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + src_row * 128);
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            cp_async16(dst + (c >> 3) * kTileB + t128_off(r, c & 7), src + c * 16, ok ? 16u : 0u);
+        }
+        cp_async_arrive_noinc(x_full(xs));
+        ++xc;
+      }
+    }
+  } else if (warp == 5) {
+    // ================================ MMA issue ================================
+    if (lane == 0) {
+      const uint32_t idesc_k = umma_idesc(128, 128, false, false);
+      const uint32_t idesc_mn = umma_idesc(128, 128, true, true);
+      uint32_t xc = 0, wc = 0, t_local = 0, acc_par = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+        const uint32_t zs = t_local % kZ;
+        mbar_wait(z_full(zs), (t_local / kZ) & 1);
+        tc_fence_after();
+        for (int b = 0; b < nblk; ++b) {
+          if (!first) {
+            mbar_wait(acc_empty, acc_par);
+            acc_par ^= 1;
+          }
+          first = false;
+          tc_fence_after();
+          for (int kb = 0; kb < 2; ++kb, ++wc) {
+            const uint32_t ws = wc % kW;
+            mbar_wait(w_full(ws), (wc / kW) & 1);
+            tc_fence_after();
+            for (int k = 0; k < 4; ++k)
+              umma(tmem, desc_kmajor(z_slot(zs) + kb * kTileB, k), desc_kmajor(w_slot(ws), k), idesc_k, (kb | k) != 0);
+            umma_commit(w_empty(ws));
+          }
+          umma_commit(acc_full);
+          const uint32_t xs = xc % kX;
+          mbar_wait(x_full(xs), (xc / kX) & 1);
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t d_w = tmem + 128u * (1 + b);
+          for (int ks = 0; ks < 8; ++ks)
+            umma(d_w, desc_mnmajor(x_slot(xs), (uint32_t)kTileB, ks), desc_mnmajor(z_slot(zs), (uint32_t)kTileB, ks),
+                 idesc_mn, (t_local | ks) != 0);
+          umma_commit(x_empty(xs));
+          ++xc;
+        }
+        umma_commit(z_empty(zs));
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    // ================================ epilogue ================================
+    const int row = tid;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t acc_par = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      int64_t row0;
+      int cnt;
+      tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
+#pragma unroll 1
+      for (int b = 0; b < nblk; ++b) {
+        mbar_wait(acc_full, acc_par);
+        acc_par ^= 1;
+        tc_fence_after();
+        named_bar_sync(1, 128);  // the previous copy-out has finished reading the staging tile
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          const uint32_t sb = s_stage + (c >> 1) * kTileB;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            st_shared_v4(sb + t128_off(row, (c & 1) * 4 + q4), pack_bf16x2(v[q4 * 8], v[q4 * 8 + 1]),
+                         pack_bf16x2(v[q4 * 8 + 2], v[q4 * 8 + 3]), pack_bf16x2(v[q4 * 8 + 4], v[q4 * 8 + 5]),
+                         pack_bf16x2(v[q4 * 8 + 6], v[q4 * 8 + 7]));
+        }
+        tc_fence_before();
+        mbar_arrive(acc_empty);
+        named_bar_sync(1, 128);
+        const int sink = p.sink[b];
+        if (sink == SINK_STORE_BF16 || sink == SINK_ADD_F32) {
+          const int cc = tid & 15, rg = tid >> 4;
+#pragma unroll 1
+          for (int i = rg; i < cnt; i += 8) {
+            const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
+            const int64_t o = (row0 + i) * 128 + cc * 8;
+            if (sink == SINK_STORE_BF16) {
+              *reinterpret_cast<uint4*>(p.bf16_dst[b] + o) = q;
+            } else {
+              const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+              float m[8];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                m[2 * e] = bf16_bits_to_float(qw[e] & 0xffffu);
+                m[2 * e + 1] = __uint_as_float(qw[e] & 0xffff0000u);
+              }
+              if (p.f32_src[b]) {
+                const float4 r0 = *reinterpret_cast<const float4*>(p.f32_src[b] + o);
+                const float4 r1 = *reinterpret_cast<const float4*>(p.f32_src[b] + o + 4);
+                m[0] += r0.x; m[1] += r0.y; m[2] += r0.z; m[3] += r0.w;
+                m[4] += r1.x; m[5] += r1.y; m[6] += r1.z; m[7] += r1.w;
+              }
+              *reinterpret_cast<float4*>(p.f32_dst[b] + o) = make_float4(m[0], m[1], m[2], m[3]);
+              *reinterpret_cast<float4*>(p.f32_dst[b] + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+            }
+          }
+        } else if (sink == SINK_SEGSUM_F32) {
+          // adjoint of the receiver gather: deterministic segmented sum over the tile's CSR rows
+          const int col = tid;
+          const uint32_t cbase = s_stage + (col >> 6) * kTileB + (col & 7) * 2;
+          const int chunk = (col & 63) >> 3;
+          const int n0 = p.tile_node_start[tile], n1 = p.tile_node_start[tile + 1];
+          int jb = p.row_ptr[n0] - (int)row0;
+          for (int v = n0; v < n1; ++v) {
+            const int je = p.row_ptr[v + 1] - (int)row0;
+            float acc = p.f32_src[b] ? p.f32_src[b][(int64_t)v * 128 + col] : 0.f;
+            for (int j = jb; j < je; ++j) {
+              uint16_t hx;
+              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(cbase + t128_off(j, chunk)));
+              acc += bf16_bits_to_float(hx);
+            }
+            p.f32_dst[b][(int64_t)v * 128 + col] = acc;
+            jb = je;
+          }
+        }
+      }
+    }
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    for (int b = 0; b < nblk; ++b) {
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(t_lane + 128u * (1 + b) + c * 32, v);
+        float4* dst = reinterpret_cast<float4*>(my_partial + (size_t)b * 16384 + (size_t)row * 128 + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 512);
+}
+}  // namespace input
+
+// ======================================================================================================
+// CUDA-core helpers
+// ======================================================================================================
+__global__ void __launch_bounds__(256) reduce_pieces_kernel(const float* __restrict__ partial, int n_parts,
+                                                            int64_t stride, const Pieces pieces, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int64_t e = i;
+  int k = 0;
+  while (k < pieces.n - 1 && e >= pieces.p[k].count) {
+    e -= pieces.p[k].count;
+    ++k;
+  }
+  const float* src = partial + pieces.p[k].src_off + e;
+  float s = 0.f;
+  for (int q = 0; q < n_parts; ++q) s += src[(int64_t)q * stride];
+  pieces.p[k].dst[e] = s;
+}
+
+// Address of element (row, col) of a [tile][2][16 KB] image, in bytes from the tile base.
+__device__ __forceinline__ uint32_t img_off(int row, int col) {
+  return (uint32_t)(col >> 6) * (uint32_t)kTileB + t128_off(row, (col & 63) >> 3) + (uint32_t)(col & 7) * 2u;
+}
+
+// One CTA per 128-row tile, thread == hidden column c.
+__global__ void __launch_bounds__(128) decoder_head_kernel(const float* __restrict__ dout, int od,
+                                                           const float* __restrict__ w_last,
+                                                           const __nv_bfloat16* __restrict__ h_img, int64_t M,
+                                                           __nv_bfloat16* __restrict__ z_img,
+                                                           float* __restrict__ partial) {
+  __shared__ float dout_s[128 * 16];
+  const int tile = blockIdx.x, c = threadIdx.x;
+  const int64_t row0 = (int64_t)tile * kTile;
+  const int cnt = (int)min((int64_t)kTile, M - row0);
+  for (int i = c; i < 128 * od; i += 128) {
+    const int r = i / od;
+    dout_s[i] = r < cnt ? dout[row0 * od + i] : 0.f;
+  }
+  float wc[16], dw[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    wc[j] = j < od ? w_last[c * od + j] : 0.f;
+    dw[j] = 0.f;
+  }
+  __syncthreads();
+  const uint8_t* hb = reinterpret_cast<const uint8_t*>(h_img) + (size_t)tile * kImg;
+  uint8_t* zb = reinterpret_cast<uint8_t*>(z_img) + (size_t)tile * kImg;
+  float dbz = 0.f;
+  for (int r = 0; r < kTile; ++r) {
+    const uint32_t off = img_off(r, c);
+    __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    if (r < cnt) {
+      const float h = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(hb + off));
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j < od) {
+          const float d = dout_s[r * od + j];
+          dot = fmaf(d, wc[j], dot);
+          dw[j] = fmaf(h, d, dw[j]);
+        }
+      z = __float2bfloat16_rn(h > 0.f ? dot : 0.f);
+      dbz += __bfloat162float(z);
+    }
+    *reinterpret_cast<__nv_bfloat16*>(zb + off) = z;
+  }
+  float* my = partial + (size_t)tile * (size_t)(128 * od + od + 128);
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+    if (j < od) my[c * od + j] = dw[j];
+  if (c < od) {
+    float s = 0.f;
+    for (int r = 0; r < cnt; ++r) s += dout_s[r * od + c];
+    my[128 * od + c] = s;
+  }
+  my[128 * od + od + c] = dbz;
+}
+
+// One CTA per tile.  Phase 1 (thread == output column): dW_0[f][c] partials.  Phase 2 (thread == row):
+// d_raw[row][f] = sum_c dZ_0[row][c] W_0[f][c].
+__global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16* __restrict__ dz0,
+                                                            const float* __restrict__ raw,
+                                                            const int32_t* __restrict__ raw_idx, int F,
+                                                            const float* __restrict__ w0, int64_t M,
+                                                            const int32_t* __restrict__ trs,
+                                                            float* __restrict__ partial, float* __restrict__ d_raw) {
+  extern __shared__ float es[];
+  float* z_s = es;               // [128][129]
+  float* x_s = es + 128 * 129;   // [128][F]
+  const int tile = blockIdx.x, t = threadIdx.x;
+  int64_t row0;
+  int cnt;
+  tile_rows(trs, M, tile, row0, cnt);
+  const uint8_t* zb = reinterpret_cast<const uint8_t*>(dz0) + (size_t)tile * kImg;
+  for (int i = t; i < 128 * 16; i += 128) {  // 16-byte chunks of the image
+    const int r = i >> 4, ch = i & 15;
+    const uint4 q = *reinterpret_cast<const uint4*>(zb + (ch >> 3) * kTileB + t128_off(r, ch & 7));
+    const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      z_s[r * 129 + ch * 8 + 2 * e] = r < cnt ? bf16_bits_to_float(qw[e] & 0xffffu) : 0.f;
+      z_s[r * 129 + ch * 8 + 2 * e + 1] = r < cnt ? __uint_as_float(qw[e] & 0xffff0000u) : 0.f;
+    }
+  }
+  for (int i = t; i < 128 * F; i += 128) {
+    const int r = i / F, f = i - r * F;
+    float v = 0.f;
+    if (r < cnt) {
+      const int64_t src = raw_idx ? (int64_t)raw_idx[row0 + r] : row0 + r;
+      v = raw[src * F + f];
+    }
+    x_s[i] = v;
+  }
+  __syncthreads();
+  float* my = partial + (size_t)tile * (size_t)F * 128;
+  for (int f0 = 0; f0 < F; f0 += 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < cnt; ++r) {
+      const float z = z_s[r * 129 + t];
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (f0 + e < F) acc[e] = fmaf(x_s[r * F + f0 + e], z, acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (f0 + e < F) my[(size_t)(f0 + e) * 128 + t] = acc[e];
+  }
+  if (d_raw && t < cnt) {
+    for (int f = 0; f < F; ++f) {
+      float s = 0.f;
+      for (int c = 0; c < 128; ++c) s = fmaf(z_s[t * 129 + c], w0[f * 128 + c], s);
+      d_raw[(row0 + t) * F + f] = s;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restrict__ d_nf,
+                                                                const __nv_bfloat16* __restrict__ dxs,
+                                                                const int32_t* __restrict__ col_ptr,
+                                                                const int32_t* __restrict__ csc_slot, int64_t N) {
+  const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (v >= N) return;
+  const int lane = threadIdx.x & 31;
+  const int cb = col_ptr[v], ce = col_ptr[v + 1];
+  float4 s = *reinterpret_cast<const float4*>(d_nf + v * 128 + lane * 4);
+  for (int j = cb; j < ce; ++j) {
+    const uint2 q = *reinterpret_cast<const uint2*>(dxs + (int64_t)csc_slot[j] * 128 + lane * 4);
+    s.x += bf16_bits_to_float(q.x & 0xffffu);
+    s.y += __uint_as_float(q.x & 0xffff0000u);
+    s.z += bf16_bits_to_float(q.y & 0xffffu);
+    s.w += __uint_as_float(q.y & 0xffff0000u);
+  }
+  *reinterpret_cast<float4*>(d_nf + v * 128 + lane * 4) = s;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+int backward_grid(int n_tiles) { return n_tiles < sm_count() ? n_tiles : sm_count(); }
+
+cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(chain::mlp_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)chain::kSmemLaunch);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = backward_grid(p.n_tiles);
+  if (grid_out) *grid_out = grid;
+  if (grid == 0) return cudaSuccess;
+  ProfScope ps(TAG_TC_MLP_BWD, st);
+  chain::mlp_bwd_chain_kernel<<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(input::mlp_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)input::kSmemLaunch);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = backward_grid(p.n_tiles);
+  if (grid_out) *grid_out = grid;
+  if (grid == 0) return cudaSuccess;
+  ProfScope ps(TAG_TC_DW, st);
+  input::mlp_bwd_input_kernel<<<grid, input::kThreads, input::kSmemLaunch, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t reduce_pieces(const float* partial, int n_parts, int64_t stride, const Pieces& pieces, cudaStream_t st) {
+  int64_t total = 0;
+  for (int i = 0; i < pieces.n; ++i) total += pieces.p[i].count;
+  if (total == 0) return cudaSuccess;
+  ProfScope ps(TAG_REDUCE_PARTIALS, st);
+  reduce_pieces_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, n_parts, stride, pieces, total);
+  return cudaGetLastError();
+}
+
+cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,
+                             int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, cudaStream_t st) {
+  if (n_tiles == 0) return cudaSuccess;
+  ProfScope ps(TAG_TC_MISC, st);
+  decoder_head_kernel<<<n_tiles, 128, 0, st>>>(dout, out_dim, w_last, h_img, M, z_img, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const int32_t* raw_idx, int F,
+                              const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
+                              float* partial, float* d_raw, cudaStream_t st) {
+  if (n_tiles == 0) return cudaSuccess;
+  const size_t smem = (size_t)(128 * 129 + 128 * F) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(encoder_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)((128 * 129 + 128 * 64) * sizeof(float)));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  ProfScope ps(TAG_TC_MISC, st);
+  encoder_input_kernel<<<n_tiles, 128, smem, st>>>(dz0, raw, raw_idx, F, w0, M, tile_row_start, partial, d_raw);
+  return cudaGetLastError();
+}
+
+cudaError_t sender_gather_add(float* d_nf, const __nv_bfloat16* dxs, const int32_t* col_ptr,
+                              const int32_t* csc_slot, int64_t N, cudaStream_t st) {
+  if (N == 0) return cudaSuccess;
+  ProfScope ps(TAG_NODE_GRAD_GATHER, st);
+  sender_gather_add_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(d_nf, dxs, col_ptr, csc_slot, N);
+  return cudaGetLastError();
+}
+
+}  // namespace tc
+}  // namespace mgn

@@ -102,6 +102,36 @@ void fill_layers(const mgn_model* m, size_t mi, const float* params, const TcWor
   p.save_rstd = training ? w.saves[mi].rstd : nullptr;
 }
 
+// Scratch of the backward pass, placed after the forward workspace.
+struct BwdScratch {
+  float *d_nf = nullptr, *d_ef = nullptr, *d_agg = nullptr;  // fp32 gradients of the latents
+  __nv_bfloat16* dxs = nullptr;                              // [E][128] sender adjoint rows (CSR order)
+  __nv_bfloat16 *dz0 = nullptr, *ztop = nullptr;             // tile images
+  float* partial = nullptr;                                  // per-CTA / per-tile weight-gradient partials
+  size_t partial_floats = 0;
+  size_t bytes = 0;
+};
+
+void bwd_layout(const mgn_model* m, const mgn_graph* g, void* base, BwdScratch& b) {
+  const int64_t N = g->N, E = g->E;
+  const int64_t node_tiles = (N + kTile - 1) / kTile, edge_tiles = g->n_edge_tiles;
+  const int64_t max_tiles = std::max<int64_t>(std::max(node_tiles, edge_tiles), 1);
+  Bump bump(base);
+  b.d_nf = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
+  b.d_ef = bump.f((size_t)std::max<int64_t>(E, 1) * 128);
+  b.d_agg = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
+  b.dxs = bump.h((size_t)std::max<int64_t>(E, 1) * 128);
+  b.dz0 = static_cast<__nv_bfloat16*>(bump.raw((size_t)max_tiles * 2 * kTileB));
+  b.ztop = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(node_tiles, 1) * 2 * kTileB));
+  const int grid = backward_grid((int)max_tiles);
+  size_t pf = (size_t)grid * std::max(chain_partial_floats(kMaxSteps), (size_t)3 * 16384);
+  pf = std::max(pf, (size_t)max_tiles * 64 * 128);                                      // encoder input layer
+  pf = std::max(pf, (size_t)node_tiles * (size_t)(128 * m->cfg.out_dim + m->cfg.out_dim + 128));  // decoder head
+  b.partial_floats = pf;
+  b.partial = bump.f(pf);
+  b.bytes = bump.off;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -150,6 +180,13 @@ int32_t tc_workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training
   size_t extra = 0;
   if (training) MGN_TRY(tc_backward_scratch_bytes(m, g, &extra));
   *bytes = w.bytes + extra;
+  return MGN_OK;
+}
+
+int32_t tc_backward_scratch_bytes(const mgn_model* m, const mgn_graph* g, size_t* bytes) {
+  BwdScratch b;
+  bwd_layout(m, g, nullptr, b);
+  *bytes = b.bytes;
   return MGN_OK;
 }
 
@@ -251,6 +288,203 @@ int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, 
     p.out_dim = m->cfg.out_dim;
     MGN_CUDA_TRY(mlp_forward_tc(p, st));
   }
+  return MGN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Backward: the Zygote pullback of mgn.model(graph, ps, st) (src/strategies.jl:189-194, :421).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct BwdCtx {
+  const mgn_model* m;
+  const mgn_graph* g;
+  const float* params;
+  float* grads;
+  TcWorkspace* w;
+  BwdScratch* b;
+  cudaStream_t st;
+};
+
+// Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
+// LayerNorm (dy = dy_a[r] + dy_b[b_idx[r]]); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
+int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const float* dy_b,
+                  const int32_t* b_idx) {
+  const MlpLayout& L = c.m->mlps[mi];
+  const MlpImages& im = c.m->images->mlps[mi];
+  const MlpSave& sv = c.w->saves[mi];
+  const int nd = L.n_dense;
+  ChainParams p{};
+  p.n_tiles = edge_rows ? c.g->n_edge_tiles : (int)((c.g->N + kTile - 1) / kTile);
+  p.M = edge_rows ? c.g->E : c.g->N;
+  p.tile_row_start = edge_rows ? c.g->tile_row_start : nullptr;
+  int top;
+  if (L.layer_norm) {
+    p.head_mode = HEAD_LN;
+    p.dy_a = dy_a;
+    p.dy_b = dy_b;
+    p.b_idx = b_idx;
+    p.xhat = sv.xhat;
+    p.rstd = sv.rstd;
+    p.ln_scale = c.params + L.ln_scale_off;
+    top = nd - 1;
+  } else {
+    p.head_mode = HEAD_IMAGE;
+    p.z_top = c.b->ztop;
+    top = nd - 2;
+  }
+  p.nsteps = top;  // layers top .. 1
+  if (p.nsteps == 0) return MGN_OK;
+  for (int j = 0; j < p.nsteps; ++j) {
+    const int l = top - j;
+    p.h_img[j] = sv.h[l - 1];
+    p.wt_img[j] = c.w->images + (size_t)im.bwd_off[l] * (kTileB / 2);
+  }
+  p.dz_out = c.b->dz0;
+  p.partial = c.b->partial;
+  int grid = 0;
+  MGN_CUDA_TRY(mlp_backward_chain_tc(p, &grid, c.st));
+  Pieces pc{};
+  const int64_t base_db = (int64_t)p.nsteps * 16384;
+  for (int j = 0; j < p.nsteps; ++j) {
+    const int l = top - j;
+    pc.p[pc.n++] = {(int64_t)j * 16384, c.grads + L.w_off[l], 16384};
+    pc.p[pc.n++] = {base_db + (int64_t)(j + 1) * 128, c.grads + L.b_off[l - 1], 128};
+  }
+  if (L.layer_norm) {
+    pc.p[pc.n++] = {base_db, c.grads + L.b_off[top], 128};
+    pc.p[pc.n++] = {base_db + (int64_t)(p.nsteps + 1) * 128, c.grads + L.ln_scale_off, 128};
+    pc.p[pc.n++] = {base_db + (int64_t)(p.nsteps + 1) * 128 + 128, c.grads + L.ln_bias_off, 128};
+  }
+  MGN_CUDA_TRY(reduce_pieces(c.b->partial, grid, (int64_t)chain_partial_floats(p.nsteps), pc, c.st));
+  return MGN_OK;
+}
+
+int32_t run_input(const BwdCtx& c, size_t mi, InputParams& p) {
+  const MlpLayout& L = c.m->mlps[mi];
+  const MlpImages& im = c.m->images->mlps[mi];
+  p.dz0 = (L.layer_norm || L.n_dense > 2) ? c.b->dz0 : c.b->ztop;
+  p.wt_img = c.w->images + (size_t)im.bwd_off[0] * (kTileB / 2);
+  p.partial = c.b->partial;
+  int grid = 0;
+  MGN_CUDA_TRY(mlp_backward_input_tc(p, &grid, c.st));
+  Pieces pc{};
+  pc.p[pc.n++] = {0, c.grads + L.w_off[0], (int64_t)p.nblk * 16384};
+  MGN_CUDA_TRY(reduce_pieces(c.b->partial, grid, (int64_t)p.nblk * 16384, pc, c.st));
+  return MGN_OK;
+}
+
+int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const float* raw, const int32_t* raw_idx,
+                          float* d_raw) {
+  const MlpLayout& L = c.m->mlps[mi];
+  const int n_tiles = edge_rows ? c.g->n_edge_tiles : (int)((c.g->N + kTile - 1) / kTile);
+  const int F = L.in[0];
+  MGN_CUDA_TRY(encoder_input_bwd(c.b->dz0, raw, raw_idx, F, c.params + L.w_off[0], n_tiles,
+                                 edge_rows ? c.g->E : c.g->N, edge_rows ? c.g->tile_row_start : nullptr,
+                                 c.b->partial, d_raw, c.st));
+  Pieces pc{};
+  pc.p[pc.n++] = {0, c.grads + L.w_off[0], (int64_t)F * 128};
+  MGN_CUDA_TRY(reduce_pieces(c.b->partial, n_tiles, (int64_t)F * 128, pc, c.st));
+  return MGN_OK;
+}
+
+}  // namespace
+
+int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                    const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                    size_t ws_bytes, cudaStream_t st) {
+  if (!g->tiles_ok)
+    return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
+  TcWorkspace w;
+  tc_layout(m, g, true, ws, w);
+  BwdScratch b;
+  bwd_layout(m, g, static_cast<char*>(ws) + w.bytes, b);
+  if (w.bytes + b.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_backward (bf16)");
+  const int64_t N = g->N, E = g->E;
+  const int mps = m->cfg.mps, nd = m->n_dense(), od = m->cfg.out_dim;
+  const int node_tiles = (int)((N + kTile - 1) / kTile);
+  BwdCtx c{m, g, params, dparams, &w, &b, st};
+
+  // ---- Decoder (no LayerNorm): last Dense on CUDA cores, the rest on the tensor cores
+  {
+    const size_t di = m->mlps.size() - 1;
+    const MlpLayout& L = m->mlps[di];
+    MGN_CUDA_TRY(decoder_head_bwd(dout, od, params + L.w_off[nd - 1], w.saves[di].h[nd - 2], node_tiles, N, b.ztop,
+                                  b.partial, st));
+    Pieces pc{};
+    pc.p[pc.n++] = {0, dparams + L.w_off[nd - 1], (int64_t)128 * od};
+    pc.p[pc.n++] = {(int64_t)128 * od, dparams + L.b_off[nd - 1], od};
+    pc.p[pc.n++] = {(int64_t)128 * od + od, dparams + L.b_off[nd - 2], 128};
+    MGN_CUDA_TRY(reduce_pieces(b.partial, node_tiles, (int64_t)128 * od + od + 128, pc, st));
+    MGN_TRY(run_chain(c, di, false, nullptr, nullptr, nullptr));
+    InputParams p{};
+    p.n_tiles = node_tiles;
+    p.M = N;
+    p.nblk = 1;
+    p.x[0] = w.nf16[mps];
+    p.sink[0] = SINK_ADD_F32;
+    p.f32_dst[0] = b.d_nf;
+    MGN_TRY(run_input(c, di, p));
+  }
+  bool d_ef_valid = false;
+  for (int k = mps - 1; k >= 0; --k) {
+    {  // node update: nf[k+1] = nf[k] + LN(MLP_n([nf[k]; agg[k]]))
+      const size_t mi = 3 + 2 * k;
+      MGN_TRY(run_chain(c, mi, false, b.d_nf, nullptr, nullptr));
+      InputParams p{};
+      p.n_tiles = node_tiles;
+      p.M = N;
+      p.nblk = 2;
+      p.x[0] = w.nf16[k];
+      p.x[1] = w.agg16[k];
+      p.sink[0] = SINK_ADD_F32;  // residual + direct path
+      p.f32_src[0] = b.d_nf;
+      p.f32_dst[0] = b.d_nf;
+      p.sink[1] = SINK_ADD_F32;  // gradient of the aggregated messages
+      p.f32_dst[1] = b.d_agg;
+      MGN_TRY(run_input(c, mi, p));
+    }
+    if (E > 0) {  // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
+      const size_t mi = 2 + 2 * k;
+      MGN_TRY(run_chain(c, mi, true, d_ef_valid ? b.d_ef : nullptr, b.d_agg, g->recv_csr));
+      InputParams p{};
+      p.n_tiles = g->n_edge_tiles;
+      p.M = E;
+      p.tile_row_start = g->tile_row_start;
+      p.tile_node_start = g->tile_node_start;
+      p.row_ptr = g->row_ptr;
+      p.nblk = 3;
+      p.x[0] = w.nf16[k];
+      p.idx[0] = g->send_csr;
+      p.x[1] = w.nf16[k];
+      p.idx[1] = g->recv_csr;
+      p.x[2] = w.ef16[k];
+      p.sink[0] = SINK_STORE_BF16;  // sender adjoint rows, gathered per node through the CSC below
+      p.bf16_dst[0] = b.dxs;
+      p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local
+      p.f32_src[1] = b.d_nf;
+      p.f32_dst[1] = b.d_nf;
+      p.sink[2] = SINK_ADD_F32;     // edge-latent residual
+      p.f32_src[2] = d_ef_valid ? b.d_ef : nullptr;
+      p.f32_dst[2] = b.d_ef;
+      MGN_TRY(run_input(c, mi, p));
+      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.dxs, g->col_ptr, g->csc_slot, N, st));
+      d_ef_valid = true;
+    }
+  }
+  // ---- Encoders
+  {
+    const MlpLayout& L = m->mlps[1];
+    if (d_ef_valid) {
+      MGN_TRY(run_chain(c, 1, true, b.d_ef, nullptr, nullptr));
+      MGN_TRY(run_encoder_input(c, 1, true, ef, g->perm, nullptr));
+    } else {
+      const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
+      MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
+    }
+  }
+  MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr));
+  MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf));
   return MGN_OK;
 }
 
