@@ -230,8 +230,7 @@ def run_ours(args, rank, world, local_rank):
         gs, loss = pkg.train_step(strat, t)
         for g in gs:
             if distributed:
-                dist.all_reduce(g)
-                g.mul_(1.0 / world)
+                pkg.allreduce_mean_(g, world)      # one NCCL all-reduce of the flat fp32 gradient
             opt.update(opt_state, mgn.ps, g)
         loss_buf.copy_(loss)
 

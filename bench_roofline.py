@@ -1,19 +1,23 @@
 """Roofline of the dominant kernel + launch count, measured live by bench.py (rank 0).
 
-A few extra, un-captured steps run with the library's launch profiler on: every launch of the
-dominant kernel family is bracketed by CUDA events on its own stream, inside the real step.
-achieved = algorithmic FLOPs (or bytes) of those launches / their summed device time.
-Algorithmic work per unit follows SURVEY.md 8d / DESIGN.md:
-  edge MLP forward : 2*D^2*(L+2) FLOP per edge          (L = hidden_layers + 2 Dense layers)
-  node MLP forward : 2*D^2*(L+1) FLOP per node
-  backward         : 2x forward (dX and dW GEMMs; recompute is NOT counted)
+A few extra, un-captured steps run with the library's launch profiler on: every launch of one
+kernel family is bracketed by CUDA events on its own stream, inside the real step.  For each
+tensor-core kernel family (fused MLP forward, backward chain, backward input layer) we report
+  achieved = algorithmic bytes (and FLOPs) of those launches / their summed device time
+against the measured peaks of MEASURED_PEAKS.json.  The algorithmic work per unit is the data
+layout of DESIGN.md section 3 (training mode, fp32 master latents + bf16 shadows):
+
+  kernel family   FLOP / edge row          FLOP / node row        bytes / edge row   bytes / node row
+  forward         2 D^2 (L+2)              2 D^2 (L+1)            2572               3076 (+512: gather source + agg)
+  bwd chain       4 D^2 (L-1)              4 D^2 (L-1)            1540 + 512(d_agg)  1540
+  bwd input       12 D^2                   8 D^2                  2056               2816
+(bytes: every tensor the kernel must read or write once per row; gathered node rows are counted
+once per node, not once per edge - they are L2 hits after the first touch.)
 """
 from __future__ import annotations
 
 import json
 import os
-
-import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 
@@ -27,40 +31,105 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def algorithmic_work(E, N, D, L, mps, node_in, edge_in, out_dim):
+    """-> {family: (flops, bytes)} for ONE training step (all launches of the family)."""
+    D2 = D * D
+    img = 2 * D                      # one bf16 row of a tile image / bf16 latent row
+    f32 = 4 * D
+    # ---- forward (training: saves L-1 hidden images + xhat + rstd)
+    saves = L * img + 4
+    f_edge = 2 * D2 * (L + 2)
+    f_node = 2 * D2 * (L + 1)
+    b_edge_fwd = img + f32 + 8 + f32 + img + saves                 # ef16, ef32 r/w, idx, ef16', saves
+    b_node_fwd = 2 * img + f32 + f32 + img + saves + 2 * img       # nf16, agg16, nf32 r/w, nf16', saves | gather src, agg write
+    fwd_flops = mps * (f_edge * E + f_node * N)
+    fwd_bytes = mps * (b_edge_fwd * E + b_node_fwd * N)
+    enc_flops = 2 * ((node_in * D + (L - 1) * D2) * N + (edge_in * D + (L - 1) * D2) * E)
+    dec_flops = 2 * ((L - 1) * D2 + D * out_dim) * N
+    fwd_flops += enc_flops + dec_flops
+    fwd_bytes += (4 * edge_in + f32 + img + saves + 4) * E + (4 * node_in + f32 + img + saves) * N
+    fwd_bytes += (img + (L - 1) * img + 4 * out_dim) * N
+    # ---- backward chain: (L-1) x (dX, dW) GEMMs; reads dy (fp32), xhat, rstd, L-1 hidden images; writes dZ0
+    c_flops_row = 4 * D2 * (L - 1)
+    c_bytes_row = f32 + img + 4 + (L - 1) * img + img
+    chain_flops = mps * c_flops_row * (E + N) + c_flops_row * (E + N) + 4 * D2 * max(L - 2, 0) * N
+    chain_bytes = mps * (c_bytes_row * (E + N) + f32 * N) + c_bytes_row * (E + N) + ((L - 1) * img + img) * N
+    # ---- backward input layer
+    i_flops = mps * (12 * D2 * E + 8 * D2 * N) + 4 * D2 * N
+    i_bytes = mps * ((img + img + 8 + 2 * f32 + img) * E + 3 * f32 * N          # dz0, ef16, idx, d_ef r/w, dxs | d_nf r/w
+                     + (img + 2 * img + 2 * f32 + f32) * N)                      # node MLP: dz0, nf16+agg16, d_nf r/w, d_agg
+    i_bytes += (img + img + f32) * N
+    return {"tc_mlp_fwd": (fwd_flops, fwd_bytes), "tc_mlp_bwd": (chain_flops, chain_bytes),
+            "tc_dw": (i_flops, i_bytes)}
+
+
+def ncu_traffic():
+    """Per-launch DRAM traffic of the kernels from the committed `ncu --set full` capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return {}
+    return {}
+
+
 def roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn=None, n_nodes=None):
     from bench import HIDDEN, LATENT, MPS
     D, L = LATENT, HIDDEN + 2
     out = {}
     if step_fn is None:
         return out
-    # launches per step
     pkg.profile_begin(-1)
     step_fn()
     n_launch, _, _, per = pkg.profile_end()
     out["gpu_launches_per_step"] = int(n_launch)
     out["launches_by_kernel"] = per
     pk = peaks()
-    fams = []
-    if args.mode == "bf16":
-        fams = [("tc_mlp_fwd", 2.0 * D * D * ((L + 2) * E + (L + 1) * n_nodes) * MPS)]
+    if args.mode != "bf16":
+        fams = {"simt_gemm_fwd": (2.0 * D * D * ((L + 2) * E + (L + 1) * n_nodes) * MPS, None)}
     else:
-        fams = [("simt_gemm_fwd", 2.0 * D * D * ((L + 2) * E + (L + 1) * n_nodes) * MPS)]
-    for name, flops in fams:
+        fams = algorithmic_work(E, n_nodes, D, L, MPS, 9, 3, 2)
+    traffic = ncu_traffic()
+    reps = 3
+    rows = []
+    for name, (flops, nbytes) in fams.items():
         if name not in per:
             continue
-        reps = 3
         pkg.profile_begin(pkg.profile_tag(name))
         for _ in range(reps):
             step_fn()
         _, k, ms, _ = pkg.profile_end()
         if k == 0 or ms <= 0:
             continue
-        tf = flops * reps / (ms * 1e-3) / 1e12
-        peak = pk["bf16_tflops_sustained"]
-        out["roofline"] = {"kernel": name, "bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s",
-                           "frac": tf / peak, "traffic": None, "launches_timed": int(k),
-                           "avg_launch_us": 1e3 * ms / k,
-                           "note": f"algorithmic fwd FLOPs of the processor blocks (encoder/decoder launches of the "
-                                   f"same family are timed but their FLOPs not counted); peak = "
-                                   f"{pk['source']} sustained bf16 (kernel timed inside a long step)"}
+        sec = ms * 1e-3 / reps                      # family time per step
+        launches = k // reps
+        tf = flops / sec / 1e12
+        row = {"kernel": name, "launches_per_step": int(launches), "ms_per_step": 1e3 * sec,
+               "avg_launch_us": 1e6 * sec / launches, "tflops": tf, "tensor_frac": tf / pk["bf16_tflops_sustained"]}
+        if nbytes is not None:
+            gbs = nbytes / sec / 1e9
+            row.update({"gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"], "alg_bytes_per_launch": nbytes / launches,
+                        "alg_flops_per_launch": flops / launches})
+        rows.append(row)
+    if not rows:
+        return out
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    top = rows[0]
+    # the binding roofline of these kernels: time at the measured HBM peak vs time at the tensor peak
+    if "gbs" in top and top["hbm_frac"] >= top["tensor_frac"]:
+        out["roofline"] = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm_gbs"],
+                           "unit": "GB/s", "frac": top["hbm_frac"],
+                           "traffic": traffic.get(top["kernel"]), "launches_timed": top["launches_per_step"] * reps,
+                           "avg_launch_us": top["avg_launch_us"], "tensor_frac": top["tensor_frac"],
+                           "note": f"dominant kernel family by time inside the step; algorithmic bytes per DESIGN.md "
+                                   f"section 3 / launch duration by CUDA events; peak = {pk['source']} HBM copy "
+                                   f"bandwidth; tensor_frac is against the {pk['source']} sustained bf16 peak"}
+    else:
+        out["roofline"] = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"],
+                           "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tensor_frac"],
+                           "traffic": traffic.get(top["kernel"]), "launches_timed": top["launches_per_step"] * reps,
+                           "avg_launch_us": top["avg_launch_us"],
+                           "note": f"peak = {pk['source']} sustained bf16 (kernel timed inside a long step)"}
+    out["kernel_families"] = rows
     return out

@@ -1,0 +1,112 @@
+# GraphNetCoreB200.jl - the binding a MeshGraphNets.jl maintainer adds to run the Encode-Process-Decode
+# hot path on libmgn_b200.so (include/mgn_b200.h).  UNTESTED HERE: this image has no Julia; the same
+# ABI is exercised from Python ctypes (meshgraphnets.jl_b200/_lib.py) and by tests/.
+#
+# It provides the GraphNetCore names MeshGraphNets.jl uses on this path (docs/src/graph_net_core.md:5-36):
+#   mgn.model(graph, ps, st)            src/solve.jl:200
+#   step!(mgn, graph, target, mask, mse_reduce)   src/strategies.jl:421
+# plus a ChainRulesCore.rrule so that Zygote / SciMLSensitivity's ZygoteVJP differentiate the model call
+# w.r.t. ps and graph.nf (src/strategies.jl:183-194).  Everything else of GraphNetCore (FeatureGraph,
+# normaliser structs, load/save!) keeps its Julia definition; only the arithmetic moves.
+module GraphNetCoreB200
+
+using CUDA, ChainRulesCore
+
+const LIB = get(ENV, "MGN_B200_LIB", "libmgn_b200.so")
+
+struct MgnConfig            # mirrors mgn_model_config
+    node_in::Int32; edge_in::Int32; out_dim::Int32; latent::Int32
+    mps::Int32; hidden_layers::Int32; ln_eps::Float32; compute_mode::Int32
+end
+
+function check(status::Int32)
+    status == 0 && return
+    buf = Vector{UInt8}(undef, 1024)
+    ccall((:mgn_last_error, LIB), Int32, (Ptr{UInt8}, Csize_t), buf, 1024)
+    error("libmgn_b200: ", unsafe_string(pointer(buf)))
+end
+
+mutable struct B200Model     # stands in for the Lux chain held in GraphNetwork.model
+    handle::Ptr{Cvoid}
+    cfg::MgnConfig
+    ws::Dict{Tuple{Ptr{Cvoid},Bool},CuVector{UInt8}}
+end
+
+function B200Model(node_in, edge_in, out_dim, mps, layer_size, hidden_layers; bf16 = true)
+    cfg = MgnConfig(node_in, edge_in, out_dim, layer_size, mps, hidden_layers, 1f-5, bf16 ? 1 : 0)
+    h = Ref{Ptr{Cvoid}}()
+    check(ccall((:mgn_model_create, LIB), Int32, (Ref{MgnConfig}, Ref{Ptr{Cvoid}}), cfg, h))
+    m = B200Model(h[], cfg, Dict())
+    finalizer(x -> ccall((:mgn_model_destroy, LIB), Int32, (Ptr{Cvoid},), x.handle), m)
+    m
+end
+
+# one mgn_graph per (senders, receivers) pair: the FeatureGraphs of a trajectory share them
+const GRAPHS = IdDict{Any,Ptr{Cvoid}}()
+function graph_handle(g)      # g::GraphNetCore.FeatureGraph
+    get!(GRAPHS, g.senders) do
+        h = Ref{Ptr{Cvoid}}()
+        check(ccall((:mgn_graph_create, LIB), Int32,
+            (Int64, Int64, CuPtr{Int32}, CuPtr{Int32}, Int32, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+            size(g.nf, 2), length(g.senders), g.senders, g.receivers, 1, CUDA.stream().handle, h))
+        h[]
+    end
+end
+
+function workspace(m::B200Model, gh, training)
+    get!(m.ws, (gh, training)) do
+        n = Ref{Csize_t}(0)
+        check(ccall((:mgn_workspace_bytes, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Csize_t}),
+            m.handle, gh, training, n))
+        CUDA.zeros(UInt8, n[])
+    end
+end
+
+# ps is the flat Float32 parameter vector (ComponentArray data); mgn_model_param_layout gives the table
+function forward(m::B200Model, g, ps::CuVector{Float32}; training = false)
+    gh = graph_handle(g); ws = workspace(m, gh, training)
+    out = CUDA.zeros(Float32, m.cfg.out_dim, size(g.nf, 2))
+    check(ccall((:mgn_forward, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         CuPtr{UInt8}, Csize_t, Int32, Ptr{Cvoid}),
+        m.handle, gh, ps, g.nf, g.ef, out, ws, length(ws), training, CUDA.stream().handle))
+    out
+end
+
+function backward(m::B200Model, g, ps, dout; want_dnf = true)
+    gh = graph_handle(g); ws = workspace(m, gh, true)
+    dps = similar(ps); dnf = want_dnf ? similar(g.nf) : CuPtr{Float32}(0)
+    check(ccall((:mgn_backward, LIB), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32},
+         CuPtr{Float32}, CuPtr{Float32}, CuPtr{UInt8}, Csize_t, Ptr{Cvoid}),
+        m.handle, gh, ps, g.nf, g.ef, dout, dps, dnf, ws, length(ws), CUDA.stream().handle))
+    dps, dnf
+end
+
+# `output, st = mgn.model(graph, ps, st)`  (src/solve.jl:200)
+(m::B200Model)(g, ps, st) = (forward(m, g, ps), st)
+
+function ChainRulesCore.rrule(m::B200Model, g, ps, st)
+    out = forward(m, g, ps; training = true)
+    function pullback(ȳ)
+        dps, dnf = backward(m, g, ps, CuArray{Float32}(unthunk(ȳ[1])))
+        g̃ = Tangent{typeof(g)}(nf = dnf)          # only node features carry the ODE state
+        return NoTangent(), g̃, dps, NoTangent()
+    end
+    (out, st), pullback
+end
+
+# GraphNetCore.step!(mgn, graph, target, mask, mse_reduce) -> (gs, loss)   (src/strategies.jl:421)
+function step!(mgn, g, target::CuMatrix{Float32}, mask::CuVector{Int32}, _loss)
+    m, ps = mgn.model, mgn.ps
+    out = forward(m, g, ps; training = true)
+    loss = CUDA.zeros(Float32, 1); dout = similar(out)
+    check(ccall((:mgn_loss_mse_masked, LIB), Int32,
+        (CuPtr{Float32}, CuPtr{Float32}, Int64, Int32, CuPtr{Int32}, Int64, Int32, CuPtr{Float32},
+         CuPtr{Float32}, Ptr{Cvoid}),
+        out, target, size(out, 2), size(out, 1), mask, length(mask), 1, loss, dout, CUDA.stream().handle))
+    dps, _ = backward(m, g, ps, dout; want_dnf = false)
+    (dps,), loss                                  # gs is iterated at src/MeshGraphNets.jl:375-377
+end
+
+end # module

@@ -5,6 +5,7 @@ core.py          host mirror of the GraphNetCore.jl names MeshGraphNets.jl calls
 graph.py         mirror of src/graph.jl      (create_base_graph, build_graph)
 solve.py         mirror of src/solve.jl      (ode_step, ode_func_eval, rollout)
 strategies.py    mirror of src/strategies.jl (DerivativeTraining step)
+parallel.py      data-parallel plumbing (window sharding, gradient / normaliser all-reduce)
 """
 from ._lib import COMPUTE_BF16, COMPUTE_FP32, LIB_PATH, MgnError, load  # noqa: F401
 from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, NormaliserOfflineMeanStd,  # noqa: F401
@@ -13,5 +14,6 @@ from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, Normalis
                    shift_one_based, step_,
                    triangles_to_edges)
 from .graph import build_graph, create_base_graph  # noqa: F401
+from .parallel import allreduce_mean_, allreduce_normaliser_, shard_windows  # noqa: F401
 from .solve import ode_func_eval, ode_step, rollout  # noqa: F401
 from .strategies import DerivativeTraining, get_delta, init_train_step, train_step  # noqa: F401

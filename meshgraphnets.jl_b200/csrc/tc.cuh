@@ -91,9 +91,15 @@ struct FwdParams {
   __nv_bfloat16* save_h[kMaxLayers - 1];  // image [tile][2 tiles]
   __nv_bfloat16* save_xhat;               // image [tile][2 tiles]
   float* save_rstd;                       // [rows]
+  unsigned long long* trace;              // debug: per-role %globaltimer stamps of CTA 0 (nullptr = off)
 };
 
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st);
+// Debug: the `skip`-th next launch of kernel family `kernel` (0 forward, 1 backward chain, 2 backward input)
+// records timestamps into d_buf [4 roles][kTraceLen] (u64 nanoseconds).
+constexpr int kTraceLen = 512;
+void set_trace(unsigned long long* d_buf, int kernel, int skip);
+unsigned long long* take_trace(int kernel);
 
 // ---- fused MLP backward ----------------------------------------------------------------------------
 // Chain kernel: LayerNorm backward (or a precomputed top-level dZ image) followed by `nsteps` steps;
@@ -122,6 +128,7 @@ struct ChainParams {
   const __nv_bfloat16* wt_img[kMaxSteps];  // step j: W_l^T image (2 tiles)
   __nv_bfloat16* dz_out;               // image of the last dZ
   float* partial;                      // [grid][chain_partial_floats(nsteps)]
+  unsigned long long* trace;           // debug (see FwdParams::trace)
 };
 // per-CTA partial layout: dW[j] at j*16384 ; db[i] at nsteps*16384 + i*128 (i = 0: top dZ, i = j+1: dZ
 // produced by step j) ; g_scale, g_bias after the db block.
@@ -148,6 +155,7 @@ struct InputParams {
   const float* f32_src[3];
   __nv_bfloat16* bf16_dst[3];
   float* partial;                      // [grid][nblk * 16384]
+  unsigned long long* trace;           // debug (see FwdParams::trace)
 };
 cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st);
 

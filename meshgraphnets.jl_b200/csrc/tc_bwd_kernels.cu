@@ -46,7 +46,8 @@ constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemH = kSmemZ + kZ * kImg;
 constexpr uint32_t kSmemW = kSmemH + kH * kImg;
 constexpr uint32_t kSmemScale = kSmemW + kW * kTileB;         // ln scale [128]
-constexpr uint32_t kSmemRed = kSmemScale + 512;               // [8][3][128] fp32
+constexpr uint32_t kSmemIdx = kSmemScale + 512;               // gather rows of the tile's dy_b, 128 ints
+constexpr uint32_t kSmemRed = kSmemIdx + 512;                 // [8][3][128] fp32
 constexpr uint32_t kSmemBar = kSmemRed + 8 * 3 * 128 * 4;
 constexpr uint32_t kNumBar = 2 * kZ + 2 * kH + 2 * kW + 4;
 constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   const uint32_t s_base = smem_u32(smem);
   float* scale_s = reinterpret_cast<float*>(smem + kSmemScale);
   float* red_s = reinterpret_cast<float*>(smem + kSmemRed);
+  int* idx_s = reinterpret_cast<int*>(smem + kSmemIdx);
   const uint32_t bar0 = s_base + kSmemBar;
   auto z_full = [&](int s) { return bar0 + 8u * s; };
   auto z_empty = [&](int s) { return bar0 + 8u * (kZ + s); };
@@ -111,6 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     // ================================ producer (one thread: bulk copies only) ========================
     if (lane == 0) {
       uint32_t hc = 0, wc = 0, t_local = 0;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         if (p.head_mode == HEAD_IMAGE) {
           const uint32_t zc = t_local * (ns + 1), s = zc % kZ;
@@ -130,6 +133,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           }
           const uint32_t s = hc % kH;
           mbar_wait(h_empty(s), ((hc / kH) & 1) ^ 1);
+          trace_ev(p.trace, 3, tn);  // P: H slot free -> load issued
           mbar_arrive_expect_tx(h_full(s), kImg);
           bulk_g2s(h_slot(s), reinterpret_cast<const uint8_t*>(p.h_img[j]) + (size_t)tile * kImg, kImg, h_full(s));
           ++hc;
@@ -143,15 +147,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       const uint32_t idesc_mn = umma_idesc(128, 128, true, true);
       uint32_t hc = 0, wc = 0, t_local = 0, acc_par = 0;
       bool first = true;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         for (int j = 0; j < ns; ++j) {
           const uint32_t zc = t_local * (ns + 1) + j, zs = zc % kZ;
+          trace_ev(p.trace, 1, tn);  // M0: step start
           mbar_wait(z_full(zs), (zc / kZ) & 1);
+          trace_ev(p.trace, 1, tn);  // M1: dZ ready
           if (!first) {  // the epilogue has drained the accumulator of the previous step
             mbar_wait(acc_empty, acc_par);
             acc_par ^= 1;
           }
           first = false;
+          trace_ev(p.trace, 1, tn);  // M2: accumulator free
           fence_proxy_async();
           tc_fence_after();
           // dX = dZ W^T : A = dZ (K-major over the layer's output features), B = W^T image tile kb
@@ -164,9 +172,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             umma_commit(w_empty(ws));
           }
           umma_commit(acc_full);
+          trace_ev(p.trace, 1, tn);  // M3: dX issued (weights were there)
           // dW += H^T dZ : both operands read MN-major (rows of the tile are the reduction index)
           const uint32_t hs = hc % kH;
           mbar_wait(h_full(hs), (hc / kH) & 1);
+          trace_ev(p.trace, 1, tn);  // M4: H ready
           tc_fence_after();
           const uint32_t d_w = tmem + 128u * (1 + j);
           for (int ks = 0; ks < 8; ++ks)
@@ -185,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     const int row = tid;
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t hc = 0, t_local = 0, acc_par = 0;
+    int tn = 0;
     float db[kMaxSteps] = {0.f, 0.f, 0.f};
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
       int64_t row0;
@@ -193,10 +204,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 #pragma unroll 1
       for (int j = 0; j < ns; ++j) {
         const uint32_t zc = t_local * (ns + 1) + j + 1, zs = zc % kZ, hs = hc % kH;
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: step start
         mbar_wait(acc_full, acc_par);
         acc_par ^= 1;
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E1: accumulator full
         mbar_wait(h_full(hs), (hc / kH) & 1);
         mbar_wait(z_empty(zs), ((zc / kZ) & 1) ^ 1);
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: H there, Z slot free
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         tc_fence_before();
         mbar_arrive(acc_empty);
         named_bar_sync(1, 128);
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: masked dZ written
         const bool last = j == ns - 1;
         if (tid == 0) {
           mbar_arrive(z_full(zs));
@@ -231,20 +246,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             bulk_commit();
           }
         }
-        // bias gradient: column sums of the bf16 dZ just written (thread == column)
+        // bias gradient: column sums of the bf16 dZ just written (thread == column; 8 loads in flight)
         {
           const int col = tid;
-          const uint32_t cbase = z_slot(zs) + (col >> 6) * kTileB + (col & 7) * 2;
+          const uint8_t* cptr = smem + kSmemZ + zs * kImg + (col >> 6) * kTileB + (col & 7) * 2;
           const int chunk = (col & 63) >> 3;
           float s = 0.f;
-          for (int r = 0; r < cnt; ++r) {
-            uint16_t hx;
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(cbase + t128_off(r, chunk)));
-            s += bf16_bits_to_float(hx);
+          for (int r0 = 0; r0 < cnt; r0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)   // rows >= cnt hold zeros
+              x[u] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cptr + t128_off(min(r0 + u, kTile - 1), chunk)));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (r0 + u < cnt) ? x[u] : 0.f;
           }
           db[j] += s;
         }
         named_bar_sync(1, 128);
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E4: column sums done
         if (tid == 0) {
           if (last) {
             bulk_wait_read0();
@@ -280,74 +299,96 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 #pragma unroll
       for (int e = 0; e < 8; ++e) sc[e] = scale_s[cc * 8 + e];
       uint32_t t_local = 0;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         int64_t row0;
         int cnt;
         tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
         const uint32_t zc = t_local * (ns + 1), zs = zc % kZ;
+        if (lt == 0) trace_ev(p.trace, 0, tn);  // L0: tile start
         if (t_local > 0) mbar_wait(head_go, (t_local - 1) & 1);
         mbar_wait(z_empty(zs), ((zc / kZ) & 1) ^ 1);
+        if (lt == 0) trace_ev(p.trace, 0, tn);  // L1: may write
         const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint32_t zb = z_slot(zs) + (cc >> 3) * kTileB;
-#pragma unroll 2
-        for (int i = rg; i < kTile; i += 8) {
-          const bool ok = i < cnt;
-          float dy[8], xh[8];
+        // gather rows of dy_b for the whole tile: one coalesced load, so that the batches below never wait on
+        // a dependent index load (the previous tile's readers are past the barrier that ended their tile)
+        if (p.dy_b) {
+          idx_s[lt] = lt < cnt ? (p.b_idx ? p.b_idx[row0 + lt] : (int)(row0 + lt)) : 0;
+          named_bar_sync(2, 128);
+        }
+#pragma unroll 1
+        for (int b0 = 0; b0 < kTile; b0 += 32) {
+          // every load of 4 rows is issued before the first use (7 x 16 B per row and thread)
+          float4 a0[4], a1[4], c0[4], c1[4];
+          uint4 xq[4];
+          float rs[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dy[e] = xh[e] = 0.f;
-          float rs = 0.f;
-          if (ok) {
-            const int64_t r = row0 + i;
-            if (p.dy_a) {
-              const float4 a0 = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
-              const float4 a1 = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
-              dy[0] = a0.x; dy[1] = a0.y; dy[2] = a0.z; dy[3] = a0.w;
-              dy[4] = a1.x; dy[5] = a1.y; dy[6] = a1.z; dy[7] = a1.w;
+          for (int u = 0; u < 4; ++u) {
+            const int i = b0 + rg + 8 * u;
+            a0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a1[u] = a0[u];
+            c0[u] = a0[u];
+            c1[u] = a0[u];
+            xq[u] = make_uint4(0u, 0u, 0u, 0u);
+            rs[u] = 0.f;
+            if (i < cnt) {
+              const int64_t r = row0 + i;
+              if (p.dy_a) {
+                a0[u] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
+                a1[u] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
+              }
+              if (p.dy_b) {
+                const int64_t br = idx_s[i];
+                c0[u] = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8);
+                c1[u] = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8 + 4);
+              }
+              xq[u] = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
+              rs[u] = p.rstd[r];
             }
-            if (p.dy_b) {
-              const int64_t br = p.b_idx ? (int64_t)p.b_idx[r] : r;
-              const float4 b0 = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8);
-              const float4 b1 = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8 + 4);
-              dy[0] += b0.x; dy[1] += b0.y; dy[2] += b0.z; dy[3] += b0.w;
-              dy[4] += b1.x; dy[5] += b1.y; dy[6] += b1.z; dy[7] += b1.w;
-            }
-            const uint4 xq = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
-            const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = b0 + rg + 8 * u;
+            const float dy[8] = {a0[u].x + c0[u].x, a0[u].y + c0[u].y, a0[u].z + c0[u].z, a0[u].w + c0[u].w,
+                                 a1[u].x + c1[u].x, a1[u].y + c1[u].y, a1[u].z + c1[u].z, a1[u].w + c1[u].w};
+            const uint32_t xw[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+            float xh[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               xh[2 * e] = bf16_bits_to_float(xw[e] & 0xffffu);
               xh[2 * e + 1] = __uint_as_float(xw[e] & 0xffff0000u);
             }
-            rs = p.rstd[r];
-          }
-          float s1 = 0.f, s2 = 0.f;
+            float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float dxh = dy[e] * sc[e];
-            s1 += dxh;
-            s2 = fmaf(dxh, xh[e], s2);
-            gb[e] += dy[e];
-            gs[e] = fmaf(dy[e], xh[e], gs[e]);
-          }
+            for (int e = 0; e < 8; ++e) {
+              const float dxh = dy[e] * sc[e];
+              s1 += dxh;
+              s2 = fmaf(dxh, xh[e], s2);
+              gb[e] += dy[e];
+              gs[e] = fmaf(dy[e], xh[e], gs[e]);
+            }
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) {
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-          }
-          const float m1 = s1 * (1.f / 128.f), m2 = s2 * (1.f / 128.f);
-          uint32_t w[4];
+            for (int o = 8; o > 0; o >>= 1) {
+              s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+              s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            const float m1 = s1 * (1.f / 128.f), m2 = s2 * (1.f / 128.f);
+            uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float a = rs * (dy[2 * e] * sc[2 * e] - m1 - xh[2 * e] * m2);
-            const float b = rs * (dy[2 * e + 1] * sc[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
-            w[e] = pack_bf16x2(a, b);
-            dbt[2 * e] += bf16_bits_to_float(w[e] & 0xffffu);
-            dbt[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            for (int e = 0; e < 4; ++e) {
+              const float a = rs[u] * (dy[2 * e] * sc[2 * e] - m1 - xh[2 * e] * m2);
+              const float b = rs[u] * (dy[2 * e + 1] * sc[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
+              w[e] = pack_bf16x2(a, b);
+              dbt[2 * e] += bf16_bits_to_float(w[e] & 0xffffu);
+              dbt[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            }
+            st_shared_v4(zb + t128_off(i, cc & 7), w[0], w[1], w[2], w[3]);
           }
-          st_shared_v4(zb + t128_off(i, cc & 7), w[0], w[1], w[2], w[3]);
         }
         fence_proxy_async();
         named_bar_sync(2, 128);
+        if (lt == 0) trace_ev(p.trace, 0, tn);  // L2: top dZ written
         if (lt == 0) {
           mbar_arrive(z_full(zs));
           mbar_arrive(z_empty(zs));  // "column sums done": the head warps keep theirs in registers
@@ -390,7 +431,8 @@ constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemX = kSmemZ + kZ * kImg;
 constexpr uint32_t kSmemW = kSmemX + kX * kImg;
 constexpr uint32_t kSmemStage = kSmemW + kW * kTileB;
-constexpr uint32_t kSmemBar = kSmemStage + kImg;
+constexpr uint32_t kSmemRp = kSmemStage + kImg;               // tile-local CSR row pointer, 132 ints
+constexpr uint32_t kSmemBar = kSmemRp + 132 * 4;
 constexpr uint32_t kNumBar = 2 * kZ + 2 * kX + 2 * kW + 3;
 constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
 constexpr uint32_t kSmemTotal = kSmemTmem + 16;
@@ -413,6 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
   auto x_slot = [&](int s) { return s_base + kSmemX + (uint32_t)s * kImg; };
   auto w_slot = [&](int s) { return s_base + kSmemW + (uint32_t)s * (uint32_t)kTileB; };
   const uint32_t s_stage = s_base + kSmemStage;
+  int* rp_s = reinterpret_cast<int*>(smem + kSmemRp);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemTmem);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -446,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
   if (warp == 4) {
     // ================================ producer ================================
     uint32_t xc = 0, wc = 0, t_local = 0;
+    int tn = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
       int64_t row0;
       int cnt;
@@ -470,21 +514,29 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         wc += 2;
         __syncwarp();
         const uint32_t xs = xc % kX;
+        if (lane == 0) trace_ev(p.trace, 3, tn);  // P0: before X slot wait
         mbar_wait(x_empty(xs), ((xc / kX) & 1) ^ 1);
+        if (lane == 0) trace_ev(p.trace, 3, tn);  // P1: slot free, gather starts
         const __nv_bfloat16* src_base = p.x[b];
         const int32_t* idx = p.idx[b];
         const uint32_t dst = x_slot(xs);
-#pragma unroll 1
+        int64_t srow[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {  // the 4 index loads of this lane are in flight together
+          const int r = lane + 32 * rr;
+          srow[rr] = r < cnt ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
+        }
+#pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
           const int r = lane + 32 * rr;
           const bool ok = r < cnt;
-          const int64_t src_row = ok ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + src_row * 128);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + srow[rr] * 128);
 #pragma unroll
           for (int c = 0; c < 16; ++c)
             cp_async16(dst + (c >> 3) * kTileB + t128_off(r, c & 7), src + c * 16, ok ? 16u : 0u);
         }
         cp_async_arrive_noinc(x_full(xs));
+        if (lane == 0) trace_ev(p.trace, 3, tn);  // P2: gather issued
         ++xc;
       }
     }
@@ -495,9 +547,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
       const uint32_t idesc_mn = umma_idesc(128, 128, true, true);
       uint32_t xc = 0, wc = 0, t_local = 0, acc_par = 0;
       bool first = true;
+      int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         const uint32_t zs = t_local % kZ;
+        trace_ev(p.trace, 1, tn);  // M0: tile start
         mbar_wait(z_full(zs), (t_local / kZ) & 1);
+        trace_ev(p.trace, 1, tn);  // M1: dZ0 there
         tc_fence_after();
         for (int b = 0; b < nblk; ++b) {
           if (!first) {
@@ -515,8 +570,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
             umma_commit(w_empty(ws));
           }
           umma_commit(acc_full);
+          trace_ev(p.trace, 1, tn);  // M2: dX issued
           const uint32_t xs = xc % kX;
           mbar_wait(x_full(xs), (xc / kX) & 1);
+          trace_ev(p.trace, 1, tn);  // M3: X block there
           fence_proxy_async();
           tc_fence_after();
           const uint32_t d_w = tmem + 128u * (1 + b);
@@ -535,16 +592,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     const int row = tid;
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t acc_par = 0;
+    int tn = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int64_t row0;
       int cnt;
       tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
 #pragma unroll 1
       for (int b = 0; b < nblk; ++b) {
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: block start
         mbar_wait(acc_full, acc_par);
         acc_par ^= 1;
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E1: accumulator full
         tc_fence_after();
         named_bar_sync(1, 128);  // the previous copy-out has finished reading the staging tile
+        if (p.sink[b] == SINK_SEGSUM_F32) {  // tile-local CSR row pointer (visible after the next barrier)
+          const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
+          if (tid <= nn) rp_s[tid] = p.row_ptr[n0 + tid] - (int)row0;
+          if (tid == 0 && nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
+        }
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           float v[32];
@@ -559,16 +624,38 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         tc_fence_before();
         mbar_arrive(acc_empty);
         named_bar_sync(1, 128);
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: staged
         const int sink = p.sink[b];
-        if (sink == SINK_STORE_BF16 || sink == SINK_ADD_F32) {
+        if (sink == SINK_STORE_BF16) {
           const int cc = tid & 15, rg = tid >> 4;
-#pragma unroll 1
+#pragma unroll 4
           for (int i = rg; i < cnt; i += 8) {
             const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
-            const int64_t o = (row0 + i) * 128 + cc * 8;
-            if (sink == SINK_STORE_BF16) {
-              *reinterpret_cast<uint4*>(p.bf16_dst[b] + o) = q;
-            } else {
+            *reinterpret_cast<uint4*>(p.bf16_dst[b] + (row0 + i) * 128 + cc * 8) = q;
+          }
+        } else if (sink == SINK_ADD_F32) {
+          // dst = src + dX, 8 rows per thread in flight (2 memory round trips per tile)
+          const int cc = tid & 15, rg = tid >> 4;
+          const float* src = p.f32_src[b];
+#pragma unroll 1
+          for (int b0 = 0; b0 < kTile; b0 += 64) {
+            float4 r0[8], r1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = b0 + rg + 8 * u;
+              r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              r1[u] = r0[u];
+              if (src && i < cnt) {
+                const int64_t o = (row0 + i) * 128 + cc * 8;
+                r0[u] = *reinterpret_cast<const float4*>(src + o);
+                r1[u] = *reinterpret_cast<const float4*>(src + o + 4);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = b0 + rg + 8 * u;
+              if (i >= cnt) continue;
+              const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
               const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
               float m[8];
 #pragma unroll
@@ -576,35 +663,54 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
                 m[2 * e] = bf16_bits_to_float(qw[e] & 0xffffu);
                 m[2 * e + 1] = __uint_as_float(qw[e] & 0xffff0000u);
               }
-              if (p.f32_src[b]) {
-                const float4 r0 = *reinterpret_cast<const float4*>(p.f32_src[b] + o);
-                const float4 r1 = *reinterpret_cast<const float4*>(p.f32_src[b] + o + 4);
-                m[0] += r0.x; m[1] += r0.y; m[2] += r0.z; m[3] += r0.w;
-                m[4] += r1.x; m[5] += r1.y; m[6] += r1.z; m[7] += r1.w;
-              }
-              *reinterpret_cast<float4*>(p.f32_dst[b] + o) = make_float4(m[0], m[1], m[2], m[3]);
-              *reinterpret_cast<float4*>(p.f32_dst[b] + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+              const int64_t o = (row0 + i) * 128 + cc * 8;
+              *reinterpret_cast<float4*>(p.f32_dst[b] + o) =
+                  make_float4(m[0] + r0[u].x, m[1] + r0[u].y, m[2] + r0[u].z, m[3] + r0[u].w);
+              *reinterpret_cast<float4*>(p.f32_dst[b] + o + 4) =
+                  make_float4(m[4] + r1[u].x, m[5] + r1[u].y, m[6] + r1[u].z, m[7] + r1[u].w);
             }
           }
         } else if (sink == SINK_SEGSUM_F32) {
           // adjoint of the receiver gather: deterministic segmented sum over the tile's CSR rows
+          // (thread == column, 8 rows in flight, adds strictly in ascending CSR slot)
           const int col = tid;
-          const uint32_t cbase = s_stage + (col >> 6) * kTileB + (col & 7) * 2;
+          const uint8_t* cptr = smem + kSmemStage + (col >> 6) * kTileB + (col & 7) * 2;
           const int chunk = (col & 63) >> 3;
           const int n0 = p.tile_node_start[tile], n1 = p.tile_node_start[tile + 1];
-          int jb = p.row_ptr[n0] - (int)row0;
-          for (int v = n0; v < n1; ++v) {
-            const int je = p.row_ptr[v + 1] - (int)row0;
-            float acc = p.f32_src[b] ? p.f32_src[b][(int64_t)v * 128 + col] : 0.f;
-            for (int j = jb; j < je; ++j) {
-              uint16_t hx;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(cbase + t128_off(j, chunk)));
-              acc += bf16_bits_to_float(hx);
+          // dst[v] (+)= segment sum.  In place (src == dst) the flush is a fire-and-forget RED: every address is
+          // written by exactly one thread of one tile, so the result is deterministic and nothing waits on a load.
+          const bool in_place = p.f32_src[b] != nullptr;
+          float* dst = p.f32_dst[b];
+          int v = n0;
+          int je = rp_s[1];
+          float acc = 0.f;
+          for (int j0 = 0; j0 < cnt; j0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              x[u] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cptr + t128_off(min(j0 + u, kTile - 1), chunk)));
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + u;
+              if (j < cnt) {
+                while (j >= je) {
+                  if (in_place) atomicAdd(dst + (int64_t)v * 128 + col, acc);
+                  else dst[(int64_t)v * 128 + col] = acc;
+                  acc = 0.f;
+                  ++v;
+                  je = rp_s[v - n0 + 1];
+                }
+                acc += x[u];
+              }
             }
-            p.f32_dst[b][(int64_t)v * 128 + col] = acc;
-            jb = je;
+          }
+          for (; v < n1; ++v) {
+            if (in_place) atomicAdd(dst + (int64_t)v * 128 + col, acc);
+            else dst[(int64_t)v * 128 + col] = acc;
+            acc = 0.f;
           }
         }
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: sink done (this thread)
       }
     }
     mbar_wait(done_bar, 0);
@@ -629,11 +735,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
 // ======================================================================================================
 // CUDA-core helpers
 // ======================================================================================================
+// Block = 32 outputs x 8 part groups: thread (x, y) sums parts y, y+8, ... of output x (coalesced across x),
+// then the 8 group sums are added in a fixed order -> deterministic, 8x the memory parallelism of a plain loop.
 __global__ void __launch_bounds__(256) reduce_pieces_kernel(const float* __restrict__ partial, int n_parts,
                                                             int64_t stride, const Pieces pieces, int64_t total) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int64_t e = i;
+  __shared__ float red[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + x;
+  int64_t e = i < total ? i : total - 1;
   int k = 0;
   while (k < pieces.n - 1 && e >= pieces.p[k].count) {
     e -= pieces.p[k].count;
@@ -641,8 +750,16 @@ __global__ void __launch_bounds__(256) reduce_pieces_kernel(const float* __restr
   }
   const float* src = partial + pieces.p[k].src_off + e;
   float s = 0.f;
-  for (int q = 0; q < n_parts; ++q) s += src[(int64_t)q * stride];
-  pieces.p[k].dst[e] = s;
+#pragma unroll 4
+  for (int q = y; q < n_parts; q += 8) s += src[(int64_t)q * stride];
+  red[y][x] = s;
+  __syncthreads();
+  if (y == 0 && i < total) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][x];
+    pieces.p[k].dst[e] = t;
+  }
 }
 
 // Address of element (row, col) of a [tile][2][16 KB] image, in bytes from the tile base.
@@ -796,6 +913,22 @@ int sm_count() {
 
 int backward_grid(int n_tiles) { return n_tiles < sm_count() ? n_tiles : sm_count(); }
 
+// ---- debug trace registry (see tc.cuh)
+static unsigned long long* g_trace_buf[3] = {nullptr, nullptr, nullptr};
+static int g_trace_skip[3] = {0, 0, 0};
+void set_trace(unsigned long long* d_buf, int kernel, int skip) {
+  if (kernel < 0 || kernel > 2) return;
+  g_trace_buf[kernel] = d_buf;
+  g_trace_skip[kernel] = skip;
+}
+unsigned long long* take_trace(int kernel) {
+  if (!g_trace_buf[kernel]) return nullptr;
+  if (g_trace_skip[kernel]-- > 0) return nullptr;
+  unsigned long long* b = g_trace_buf[kernel];
+  g_trace_buf[kernel] = nullptr;
+  return b;
+}
+
 cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
@@ -808,7 +941,9 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
   if (grid_out) *grid_out = grid;
   if (grid == 0) return cudaSuccess;
   ProfScope ps(TAG_TC_MLP_BWD, st);
-  chain::mlp_bwd_chain_kernel<<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(p);
+  ChainParams q = p;
+  q.trace = take_trace(1);
+  chain::mlp_bwd_chain_kernel<<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(q);
   return cudaGetLastError();
 }
 
@@ -824,7 +959,9 @@ cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStrea
   if (grid_out) *grid_out = grid;
   if (grid == 0) return cudaSuccess;
   ProfScope ps(TAG_TC_DW, st);
-  input::mlp_bwd_input_kernel<<<grid, input::kThreads, input::kSmemLaunch, st>>>(p);
+  InputParams q = p;
+  q.trace = take_trace(2);
+  input::mlp_bwd_input_kernel<<<grid, input::kThreads, input::kSmemLaunch, st>>>(q);
   return cudaGetLastError();
 }
 
@@ -833,7 +970,7 @@ cudaError_t reduce_pieces(const float* partial, int n_parts, int64_t stride, con
   for (int i = 0; i < pieces.n; ++i) total += pieces.p[i].count;
   if (total == 0) return cudaSuccess;
   ProfScope ps(TAG_REDUCE_PARTIALS, st);
-  reduce_pieces_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, n_parts, stride, pieces, total);
+  reduce_pieces_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(partial, n_parts, stride, pieces, total);
   return cudaGetLastError();
 }
 

@@ -26,7 +26,8 @@ constexpr uint32_t kSmemRing = 0;
 constexpr uint32_t kSmemH = kRing * kTileB;                  // 2 tiles: hidden activation / xhat
 constexpr uint32_t kSmemBias = kSmemH + 2 * kTileB;          // [kMaxLayers][128] fp32
 constexpr uint32_t kSmemLn = kSmemBias + kMaxLayers * 512;   // scale[128], bias[128]
-constexpr uint32_t kSmemBar = kSmemLn + 1024;                // full[4], empty[4], acc_full, epi_done
+constexpr uint32_t kSmemRp = kSmemLn + 1024;                 // tile-local CSR row pointer, 132 ints
+constexpr uint32_t kSmemBar = kSmemRp + 132 * 4;             // full[4], empty[4], acc_full, epi_done
 constexpr uint32_t kSmemTmem = kSmemBar + 16 * 8;
 constexpr uint32_t kSmemTotal = kSmemTmem + 16;
 constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;          // slack for the 1024 B alignment
@@ -89,6 +90,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
   const uint32_t s_ring = s_base + kSmemRing, s_h = s_base + kSmemH;
   float* bias_s = reinterpret_cast<float*>(smem + kSmemBias);
   float* ln_s = reinterpret_cast<float*>(smem + kSmemLn);
+  int* rp_s = reinterpret_cast<int*>(smem + kSmemRp);
   const uint32_t bar0 = s_base + kSmemBar;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
@@ -124,24 +126,39 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
   if (warp == 4) {
     // ================================ producer ================================
     uint32_t it = 0;
+    int tn = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int64_t row0;
       int cnt;
       tile_rows(p, tile, row0, cnt);
+      // source rows of this lane's 4 tile rows, for both gather index vectors: all index loads of the tile
+      // are issued together, so no K-block waits on a dependent index load
+      int64_t src0[4], src1[4];
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const int r = lane + 32 * rr;
+        const bool ok = r < cnt;
+        const int32_t* i0 = p.in_mode == IN_RAW ? p.raw_idx : (p.in_mode == IN_GATHER3 ? p.idx0 : nullptr);
+        const int32_t* i1 = p.in_mode == IN_GATHER3 ? p.idx1 : nullptr;
+        src0[rr] = ok ? (i0 ? (int64_t)i0[row0 + r] : row0 + r) : 0;
+        src1[rr] = ok ? (i1 ? (int64_t)i1[row0 + r] : row0 + r) : 0;
+      }
       for (int l = 0; l < L; ++l) {
         for (int kb = 0; kb < p.nkb[l]; ++kb) {
           if (l == 0) {
             // ---- A tile kb of the layer-0 operand
             const int s = it % kRing;
+            if (lane == 0) trace_ev(p.trace, 3, tn);  // P0: before slot wait (A tile)
             mbar_wait(empty_bar(s), ((it / kRing) & 1) ^ 1);
+            if (lane == 0) trace_ev(p.trace, 3, tn);  // P1: slot free
             const uint32_t dst = s_ring + s * kTileB;
             if (p.in_mode == IN_RAW) {
-#pragma unroll 1
+#pragma unroll
               for (int rr = 0; rr < 4; ++rr) {
                 const int r = lane + 32 * rr;
                 const bool ok = r < cnt;
-                const int64_t src_row = ok ? (p.raw_idx ? (int64_t)p.raw_idx[row0 + r] : row0 + r) : 0;
-#pragma unroll
+                const int64_t src_row = src0[rr];
+#pragma unroll 1
                 for (int c = 0; c < 8; ++c) {
                   float v[8];
 #pragma unroll
@@ -157,19 +174,19 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
               mbar_arrive(full_bar(s));
             } else {
               const __nv_bfloat16* src_base;
-              const int32_t* idx = nullptr;
               const int seg = kb >> 1;
+              int which = 2;  // 0: rows src0, 1: rows src1, 2: identity
               if (p.in_mode == IN_GATHER3) {
                 src_base = seg == 2 ? p.x2 : p.x0;
-                idx = seg == 0 ? p.idx0 : (seg == 1 ? p.idx1 : nullptr);
+                which = seg;
               } else {
                 src_base = seg == 0 ? p.x0 : p.x1;
               }
-#pragma unroll 1
+#pragma unroll
               for (int rr = 0; rr < 4; ++rr) {
                 const int r = lane + 32 * rr;
                 const bool ok = r < cnt;
-                const int64_t src_row = ok ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
+                const int64_t src_row = ok ? (which == 0 ? src0[rr] : (which == 1 ? src1[rr] : row0 + r)) : 0;
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + src_row * 128 + (kb & 1) * 64);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) cp_async16(dst + t128_off(r, c), src + c * 16, ok ? 16u : 0u);
@@ -198,15 +215,18 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
     if (lane == 0) {
       uint32_t it = 0, epi_par = 0;
       bool first = true;
+      int tn = 0;
       const uint32_t idesc_full = umma_idesc(128, 128, false, false);
       const uint32_t idesc_last = p.fin_mode == FIN_LINEAR ? umma_idesc(128, 16, false, false) : idesc_full;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int l = 0; l < L; ++l) {
+          trace_ev(p.trace, 1, tn);  // M0: layer start
           if (!first) {  // TMEM drained and (l > 0) the next A operand written by the epilogue
             mbar_wait(epi_done, epi_par);
             epi_par ^= 1;
           }
           first = false;
+          trace_ev(p.trace, 1, tn);  // M1: epilogue of the previous layer done
           tc_fence_after();
           const uint32_t idesc = l == L - 1 ? idesc_last : idesc_full;
           const int ksteps = l == 0 ? p.ksteps0 : 4;
@@ -230,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
             if (l == 0) umma_commit(empty_bar(sa));
           }
           umma_commit(acc_full);
+          trace_ev(p.trace, 1, tn);  // M2: layer issued (operands were there)
         }
       }
     }
@@ -237,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
     // ================================ epilogue (thread == row) ================================
     uint32_t acc_par = 0;
     bool store_pending = false;
+    int tn = 0;
     const int row = tid;  // 0..127
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -244,8 +266,10 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
       int cnt;
       tile_rows(p, tile, row0, cnt);
       for (int l = 0; l < L; ++l) {
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: layer start
         mbar_wait(acc_full, acc_par);
         acc_par ^= 1;
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E1: accumulator full
         tc_fence_after();
         const bool last = l == L - 1;
         if (last && p.fin_mode == FIN_LINEAR) {
@@ -264,6 +288,12 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
           store_pending = false;
         }
         named_bar_sync(1, 128);
+        if (l == 0 && p.fin_mode == FIN_LN_RESID_AGG) {
+          // tile-local CSR row pointer -> shared memory (read by the aggregation after two more barriers)
+          const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
+          if (tid <= nn) rp_s[tid] = p.row_ptr[n0 + tid] - (int)row0;
+          if (tid == 0 && nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
+        }
         float mean = 0.f, rstd = 1.f;
         if (last) {  // LayerNorm statistics: two extra passes over TMEM (cheap), biased variance
           float s = 0.f;
@@ -330,12 +360,15 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         // ---- last layer: TMEM is drained -> the MMA warp may start the next tile
         mbar_arrive(epi_done);
         named_bar_sync(1, 128);
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: LayerNorm done, xhat staged
         if (save && tid == 0) {
           bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
           bulk_commit();
           store_pending = true;
         }
-        // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced)
+        // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced).
+        //      Rows are handled 8 at a time per thread so that all residual loads of a batch are in flight
+        //      together (2 memory round trips per tile instead of 16).
         {
           const int cc = tid & 15, rg = tid >> 4;
           float sc[8], bi[8];
@@ -344,55 +377,88 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
             sc[j] = ln_s[cc * 8 + j];
             bi[j] = ln_s[128 + cc * 8 + j];
           }
+          const bool resid = p.fin_mode != FIN_LN;
 #pragma unroll 1
-          for (int i = rg; i < cnt; i += 8) {
-            const uint4 xq = ld_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7));
-            const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
-            float m[8];
+          for (int b0 = 0; b0 < kTile; b0 += 64) {
+            float4 r0[8], r1[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
-              m[2 * j] = fmaf(__low2float(h), sc[2 * j], bi[2 * j]);
-              m[2 * j + 1] = fmaf(__high2float(h), sc[2 * j + 1], bi[2 * j + 1]);
+            for (int u = 0; u < 8; ++u) {
+              const int i = b0 + rg + 8 * u;
+              r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              r1[u] = r0[u];
+              if (resid && i < cnt) {
+                const int64_t o = (row0 + i) * 128 + cc * 8;
+                r0[u] = *reinterpret_cast<const float4*>(p.lat_in + o);
+                r1[u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+              }
             }
-            const int64_t o = (row0 + i) * 128 + cc * 8;
-            if (p.fin_mode != FIN_LN) {
-              const float4 r0 = *reinterpret_cast<const float4*>(p.lat_in + o);
-              const float4 r1 = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
-              m[0] += r0.x; m[1] += r0.y; m[2] += r0.z; m[3] += r0.w;
-              m[4] += r1.x; m[5] += r1.y; m[6] += r1.z; m[7] += r1.w;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = b0 + rg + 8 * u;
+              if (i >= cnt) continue;
+              const uint4 xq = ld_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7));
+              const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+              float m[8];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
+                m[2 * j] = fmaf(__low2float(h), sc[2 * j], bi[2 * j]);
+                m[2 * j + 1] = fmaf(__high2float(h), sc[2 * j + 1], bi[2 * j + 1]);
+              }
+              m[0] += r0[u].x; m[1] += r0[u].y; m[2] += r0[u].z; m[3] += r0[u].w;
+              m[4] += r1[u].x; m[5] += r1[u].y; m[6] += r1[u].z; m[7] += r1[u].w;
+              const int64_t o = (row0 + i) * 128 + cc * 8;
+              *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
+              *reinterpret_cast<float4*>(p.lat_out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+              uint4 bq;
+              bq.x = pack_bf16x2(m[0], m[1]);
+              bq.y = pack_bf16x2(m[2], m[3]);
+              bq.z = pack_bf16x2(m[4], m[5]);
+              bq.w = pack_bf16x2(m[6], m[7]);
+              *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
             }
-            *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
-            *reinterpret_cast<float4*>(p.lat_out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
-            uint4 bq;
-            bq.x = pack_bf16x2(m[0], m[1]);
-            bq.y = pack_bf16x2(m[2], m[3]);
-            bq.z = pack_bf16x2(m[4], m[5]);
-            bq.w = pack_bf16x2(m[6], m[7]);
-            *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
+            if (tid == 0) trace_ev(p.trace, 0, tn);  // C: one copy-out batch done
           }
         }
         // ---- deterministic segmented sum of the (pre-residual) messages: thread == column, rows in
-        //      ascending CSR slot = ascending original edge id (the CPU scatter order, a11)
+        //      ascending CSR slot = ascending original edge id (the CPU scatter order, a11).  The column is
+        //      read 8 rows at a time (loads in flight together); the adds stay strictly sequential.
         if (p.fin_mode == FIN_LN_RESID_AGG) {
           const int col = tid;
           const float sc = ln_s[col], bi = ln_s[128 + col];
-          const uint32_t cbase = s_h + (col >> 6) * kTileB + (col & 7) * 2;
+          const uint8_t* cptr = smem + kSmemH + (col >> 6) * kTileB + (col & 7) * 2;
           const int chunk = (col & 63) >> 3;
           const int n0 = p.tile_node_start[tile], n1 = p.tile_node_start[tile + 1];
-          int jb = p.row_ptr[n0] - (int)row0;
-          for (int v = n0; v < n1; ++v) {
-            const int je = p.row_ptr[v + 1] - (int)row0;
-            float acc = 0.f;
-            for (int j = jb; j < je; ++j) {
-              uint16_t hx;
-              asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hx) : "r"(cbase + t128_off(j, chunk)));
-              acc += fmaf(__bfloat162float(__ushort_as_bfloat16(hx)), sc, bi);
+          int v = n0;
+          int je = rp_s[1];                        // end of node v's segment (tile-local row)
+          float acc = 0.f;
+          for (int j0 = 0; j0 < cnt; j0 += 8) {
+            float x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = min(j0 + u, kTile - 1);
+              x[u] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cptr + t128_off(j, chunk)));
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + u;
+              if (j < cnt) {
+                while (j >= je) {  // node v has no more rows: flush (also covers nodes without in-edges)
+                  p.agg_bf16[(int64_t)v * 128 + col] = __float2bfloat16_rn(acc);
+                  acc = 0.f;
+                  ++v;
+                  je = rp_s[v - n0 + 1];
+                }
+                acc += fmaf(x[u], sc, bi);
+              }
+            }
+          }
+          for (; v < n1; ++v) {  // last node with rows, then trailing nodes without in-edges
             p.agg_bf16[(int64_t)v * 128 + col] = __float2bfloat16_rn(acc);
-            jb = je;
+            acc = 0.f;
           }
         }
+        if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: copy-out + aggregation done (this thread)
       }
     }
     if (tid == 0 && store_pending) bulk_wait0();
@@ -425,7 +491,9 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
   }
   const int grid = p.n_tiles < 2 * n_sm ? p.n_tiles : 2 * n_sm;
   ProfScope ps(TAG_TC_MLP_FWD, st);
-  mlp_fwd_kernel<<<grid, kThreads, kSmemLaunch, st>>>(p);
+  FwdParams q = p;
+  q.trace = take_trace(0);
+  mlp_fwd_kernel<<<grid, kThreads, kSmemLaunch, st>>>(q);
   return cudaGetLastError();
 }
 

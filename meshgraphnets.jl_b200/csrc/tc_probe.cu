@@ -5,6 +5,7 @@
 // with K a multiple of 64 (<= 256).  Exercised by tests/test_gpu_tc_probe.py against torch.
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include "tc.cuh"
 
 namespace mgn {
 namespace {
@@ -102,5 +103,12 @@ extern "C" int32_t mgn_debug_umma_probe(const void* d_a, const void* d_b, float*
   umma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(d_a), static_cast<const __nv_bfloat16*>(d_b), d_out, K, mode);
   MGN_CUDA_TRY(cudaGetLastError());
+  return MGN_OK;
+}
+
+// Debug: arm the per-role timestamp trace of the `skip`-th next launch of a tensor-core kernel family
+// (0 forward, 1 backward chain, 2 backward input).  d_buf: 4 * 512 u64, zeroed by the caller.
+extern "C" int32_t mgn_debug_trace(void* d_buf, int32_t kernel, int32_t skip) {
+  mgn::tc::set_trace(static_cast<unsigned long long*>(d_buf), kernel, skip);
   return MGN_OK;
 }

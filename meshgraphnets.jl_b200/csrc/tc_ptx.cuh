@@ -173,6 +173,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- debug trace ----------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// One thread per role calls this; n is the role's private event counter.
+__device__ __forceinline__ void trace_ev(unsigned long long* buf, int role, int& n) {
+  if (buf != nullptr && blockIdx.x == 0 && n < 512) buf[role * 512 + n++] = globaltimer_ns();
+}
+
 // ---- T128 addressing ----------------------------------------------------------------------------
 // Byte offset of the 16-byte chunk `chunk` (0..7) of row `row` inside a T128 tile.
 __device__ __forceinline__ uint32_t t128_off(int row, int chunk) {
