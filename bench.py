@@ -27,6 +27,16 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner on fd 1) must not get in
+# the way: fd 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 MPS, LATENT, HIDDEN = 15, 128, 2
 NX, NY = 65, 29            # N = 1885, E = 10936
 T_FRAMES = 64              # synthetic trajectory frames resident per rank
@@ -178,7 +188,7 @@ def run_reference(args, rank):
                          "sample": f"{n} derivative-training steps (fwd+bwd+Adam), batch 1, {el:.1f} s"},
         "e2e": {"value": edges_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -224,19 +234,19 @@ def run_ours(args, rank, world, local_rank):
     if distributed:
         import torch.distributed as dist
 
-    def step_body():
+    def step_body(collective=True):
         t = pkg.init_train_step(strat, (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders,
                                         receivers, 1, mask, None))
         gs, loss = pkg.train_step(strat, t)
         for g in gs:
-            if distributed:
+            if distributed and collective:
                 pkg.allreduce_mean_(g, world)      # one NCCL all-reduce of the flat fp32 gradient
             opt.update(opt_state, mgn.ps, g)
         loss_buf.copy_(loss)
 
     # ---- optional CUDA graph of the step (all library calls only enqueue on the current stream)
     graph = None
-    use_graph = (not args.no_graph) and not distributed
+    use_graph = not args.no_graph          # NCCL collectives are capturable: the DP step is one graph too
     torch.cuda.synchronize()
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
@@ -319,12 +329,12 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "clocks": clocks, "final_loss": final_loss,
     }
-    def plain_step():
+    def plain_step():  # rank 0 only (kernel-family timing): no collective, the other ranks have left
         s_cur.copy_(d_cur[0]); s_nxt.copy_(d_nxt[0])
-        step_body()
+        step_body(collective=False)
     line.update(extra_measurements(args, pkg, model, mgn, E, B, dev, plain_step, N * B))
     line["gpu_launches"] = line.get("gpu_launches_per_step", 0) * args.steps
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def extra_measurements(args, pkg, model, mgn, E, B, dev, step_fn, n_nodes):

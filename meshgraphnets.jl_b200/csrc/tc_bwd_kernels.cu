@@ -40,7 +40,9 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __
 // Chain kernel
 // ======================================================================================================
 namespace chain {
-constexpr int kThreads = 320;  // warps 0-3 epilogue, 4-7 head (LayerNorm backward), 8 producer, 9 MMA
+constexpr int kThreads = 448;  // warps 0-3 epilogue, 4-11 head (LayerNorm backward), 12 producer, 13 MMA
+constexpr int kHeadThreads = 256;
+constexpr int kWarpP = 12, kWarpM = 13;
 constexpr int kZ = 3, kH = 2, kW = 3;
 constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemH = kSmemZ + kZ * kImg;
@@ -103,13 +105,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     mbar_init(head_go, 1);
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kWarpP) {
     // ================================ producer (one thread: bulk copies only) ========================
     if (lane == 0) {
       uint32_t hc = 0, wc = 0, t_local = 0;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kWarpM) {
     // ================================ MMA issue ================================
     if (lane == 0) {
       const uint32_t idesc_k = umma_idesc(128, 128, false, false);
@@ -290,8 +292,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     }
     if (tid == 0) bulk_wait0();
   } else {
-    // ================================ head: LayerNorm backward (16 lanes per row) ================================
-    const int lt = tid - 128, cc = lt & 15, rg = lt >> 4;
+    // ================================ head: LayerNorm backward (16 lanes per row, 16 rows in flight per pass) =====
+    const int lt = tid - 128, cc = lt & 15, rg = lt >> 4;  // rg in [0, 16)
     float gs[8], gb[8], dbt[8], sc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) gs[e] = gb[e] = dbt[e] = 0.f;
@@ -314,18 +316,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         // gather rows of dy_b for the whole tile: one coalesced load, so that the batches below never wait on
         // a dependent index load (the previous tile's readers are past the barrier that ended their tile)
         if (p.dy_b) {
-          idx_s[lt] = lt < cnt ? (p.b_idx ? p.b_idx[row0 + lt] : (int)(row0 + lt)) : 0;
-          named_bar_sync(2, 128);
+          if (lt < kTile) idx_s[lt] = lt < cnt ? (p.b_idx ? p.b_idx[row0 + lt] : (int)(row0 + lt)) : 0;
+          named_bar_sync(2, kHeadThreads);
         }
 #pragma unroll 1
-        for (int b0 = 0; b0 < kTile; b0 += 32) {
+        for (int b0 = 0; b0 < kTile; b0 += 64) {
           // every load of 4 rows is issued before the first use (7 x 16 B per row and thread)
           float4 a0[4], a1[4], c0[4], c1[4];
           uint4 xq[4];
           float rs[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int i = b0 + rg + 8 * u;
+            const int i = b0 + rg + 16 * u;
             a0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             a1[u] = a0[u];
             c0[u] = a0[u];
@@ -349,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int i = b0 + rg + 8 * u;
+            const int i = b0 + rg + 16 * u;
             const float dy[8] = {a0[u].x + c0[u].x, a0[u].y + c0[u].y, a0[u].z + c0[u].z, a0[u].w + c0[u].w,
                                  a1[u].x + c1[u].x, a1[u].y + c1[u].y, a1[u].z + c1[u].z, a1[u].w + c1[u].w};
             const uint32_t xw[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           }
         }
         fence_proxy_async();
-        named_bar_sync(2, 128);
+        named_bar_sync(2, kHeadThreads);
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L2: top dZ written
         if (lt == 0) {
           mbar_arrive(z_full(zs));
@@ -395,29 +397,40 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         }
       }
     }
-    // ---- reduce the per-row-group column sums: [8][3][128] -> [3][128]
+    // ---- reduce the per-row-group column sums: the two row groups of a warp by shuffle, then [8][3][128] -> [3][128]
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      red_s[(rg * 3 + 0) * 128 + cc * 8 + e] = dbt[e];
-      red_s[(rg * 3 + 1) * 128 + cc * 8 + e] = gs[e];
-      red_s[(rg * 3 + 2) * 128 + cc * 8 + e] = gb[e];
+      dbt[e] += __shfl_xor_sync(0xffffffffu, dbt[e], 16);
+      gs[e] += __shfl_xor_sync(0xffffffffu, gs[e], 16);
+      gb[e] += __shfl_xor_sync(0xffffffffu, gb[e], 16);
     }
-    named_bar_sync(2, 128);
-    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    if ((lt & 16) == 0) {
+      const int wg = lt >> 5;  // head warp 0..7
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      t0 += red_s[(g * 3 + 0) * 128 + lt];
-      t1 += red_s[(g * 3 + 1) * 128 + lt];
-      t2 += red_s[(g * 3 + 2) * 128 + lt];
+      for (int e = 0; e < 8; ++e) {
+        red_s[(wg * 3 + 0) * 128 + cc * 8 + e] = dbt[e];
+        red_s[(wg * 3 + 1) * 128 + cc * 8 + e] = gs[e];
+        red_s[(wg * 3 + 2) * 128 + cc * 8 + e] = gb[e];
+      }
     }
-    float* tail = my_partial + (size_t)ns * 16384;
-    tail[lt] = t0;                                 // db of the top layer
-    tail[(size_t)(ns + 1) * 128 + lt] = t1;        // g_scale
-    tail[(size_t)(ns + 1) * 128 + 128 + lt] = t2;  // g_bias
+    named_bar_sync(2, kHeadThreads);
+    if (lt < 128) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        t0 += red_s[(g * 3 + 0) * 128 + lt];
+        t1 += red_s[(g * 3 + 1) * 128 + lt];
+        t2 += red_s[(g * 3 + 2) * 128 + lt];
+      }
+      float* tail = my_partial + (size_t)ns * 16384;
+      tail[lt] = t0;                                 // db of the top layer
+      tail[(size_t)(ns + 1) * 128 + lt] = t1;        // g_scale
+      tail[(size_t)(ns + 1) * 128 + 128 + lt] = t2;  // g_bias
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem, 512);
+  if (warp == kWarpM) tmem_dealloc(tmem, 512);
 }
 }  // namespace chain
 
@@ -671,44 +684,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
             }
           }
         } else if (sink == SINK_SEGSUM_F32) {
-          // adjoint of the receiver gather: deterministic segmented sum over the tile's CSR rows
-          // (thread == column, 8 rows in flight, adds strictly in ascending CSR slot)
-          const int col = tid;
-          const uint8_t* cptr = smem + kSmemStage + (col >> 6) * kTileB + (col & 7) * 2;
-          const int chunk = (col & 63) >> 3;
-          const int n0 = p.tile_node_start[tile], n1 = p.tile_node_start[tile + 1];
-          // dst[v] (+)= segment sum.  In place (src == dst) the flush is a fire-and-forget RED: every address is
-          // written by exactly one thread of one tile, so the result is deterministic and nothing waits on a load.
+          // adjoint of the receiver gather: deterministic segmented sum over the tile's CSR rows.  In place
+          // (src == dst) the flush is a fire-and-forget RED: every address is touched by exactly one thread of one
+          // tile, so the result is deterministic and nothing waits on a load.
+          const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
           const bool in_place = p.f32_src[b] != nullptr;
-          float* dst = p.f32_dst[b];
-          int v = n0;
-          int je = rp_s[1];
-          float acc = 0.f;
-          for (int j0 = 0; j0 < cnt; j0 += 8) {
-            float x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-              x[u] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cptr + t128_off(min(j0 + u, kTile - 1), chunk)));
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = j0 + u;
-              if (j < cnt) {
-                while (j >= je) {
-                  if (in_place) atomicAdd(dst + (int64_t)v * 128 + col, acc);
-                  else dst[(int64_t)v * 128 + col] = acc;
-                  acc = 0.f;
-                  ++v;
-                  je = rp_s[v - n0 + 1];
-                }
-                acc += x[u];
-              }
-            }
-          }
-          for (; v < n1; ++v) {
-            if (in_place) atomicAdd(dst + (int64_t)v * 128 + col, acc);
-            else dst[(int64_t)v * 128 + col] = acc;
-            acc = 0.f;
-          }
+          float* dst = p.f32_dst[b] + (int64_t)n0 * 128;
+          segsum_tile<false>(smem + kSmemStage, rp_s, nn, tid, 1.f, 1.f, 0.f, 0.f,
+                             [&](int v, int col, float s0, float s1) {
+                               float* d = dst + (int64_t)v * 128 + col;
+                               if (in_place) {
+                                 atomicAdd(d, s0);
+                                 atomicAdd(d + 1, s1);
+                               } else {
+                                 *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
+                               }
+                             });
         }
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: sink done (this thread)
       }

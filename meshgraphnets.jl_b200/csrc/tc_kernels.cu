@@ -294,6 +294,24 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
           if (tid <= nn) rp_s[tid] = p.row_ptr[n0 + tid] - (int)row0;
           if (tid == 0 && nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
         }
+        // residual rows of the first copy-out batch: issued now so that their latency hides behind the LayerNorm
+        float4 r0[8], r1[8];
+        const int cc = tid & 15, rg = tid >> 4;
+        const bool resid = p.fin_mode != FIN_LN;
+        auto issue_residual = [&](int b0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = b0 + rg + 8 * u;
+            r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r1[u] = r0[u];
+            if (resid && i < cnt) {
+              const int64_t o = (row0 + i) * 128 + cc * 8;
+              r0[u] = *reinterpret_cast<const float4*>(p.lat_in + o);
+              r1[u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+            }
+          }
+        };
+        if (last) issue_residual(0);
         float mean = 0.f, rstd = 1.f;
         if (last) {  // LayerNorm statistics: two extra passes over TMEM (cheap), biased variance
           float s = 0.f;
@@ -370,28 +388,15 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         //      Rows are handled 8 at a time per thread so that all residual loads of a batch are in flight
         //      together (2 memory round trips per tile instead of 16).
         {
-          const int cc = tid & 15, rg = tid >> 4;
           float sc[8], bi[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             sc[j] = ln_s[cc * 8 + j];
             bi[j] = ln_s[128 + cc * 8 + j];
           }
-          const bool resid = p.fin_mode != FIN_LN;
 #pragma unroll 1
           for (int b0 = 0; b0 < kTile; b0 += 64) {
-            float4 r0[8], r1[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = b0 + rg + 8 * u;
-              r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              r1[u] = r0[u];
-              if (resid && i < cnt) {
-                const int64_t o = (row0 + i) * 128 + cc * 8;
-                r0[u] = *reinterpret_cast<const float4*>(p.lat_in + o);
-                r1[u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
-              }
-            }
+            if (b0 != 0) issue_residual(b0);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const int i = b0 + rg + 8 * u;
@@ -424,39 +429,13 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         //      ascending CSR slot = ascending original edge id (the CPU scatter order, a11).  The column is
         //      read 8 rows at a time (loads in flight together); the adds stay strictly sequential.
         if (p.fin_mode == FIN_LN_RESID_AGG) {
-          const int col = tid;
-          const float sc = ln_s[col], bi = ln_s[128 + col];
-          const uint8_t* cptr = smem + kSmemH + (col >> 6) * kTileB + (col & 7) * 2;
-          const int chunk = (col & 63) >> 3;
-          const int n0 = p.tile_node_start[tile], n1 = p.tile_node_start[tile + 1];
-          int v = n0;
-          int je = rp_s[1];                        // end of node v's segment (tile-local row)
-          float acc = 0.f;
-          for (int j0 = 0; j0 < cnt; j0 += 8) {
-            float x[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = min(j0 + u, kTile - 1);
-              x[u] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cptr + t128_off(j, chunk)));
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = j0 + u;
-              if (j < cnt) {
-                while (j >= je) {  // node v has no more rows: flush (also covers nodes without in-edges)
-                  p.agg_bf16[(int64_t)v * 128 + col] = __float2bfloat16_rn(acc);
-                  acc = 0.f;
-                  ++v;
-                  je = rp_s[v - n0 + 1];
-                }
-                acc += fmaf(x[u], sc, bi);
-              }
-            }
-          }
-          for (; v < n1; ++v) {  // last node with rows, then trailing nodes without in-edges
-            p.agg_bf16[(int64_t)v * 128 + col] = __float2bfloat16_rn(acc);
-            acc = 0.f;
-          }
+          const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
+          const int c2 = 2 * (tid & 63);
+          __nv_bfloat16* agg = p.agg_bf16 + (int64_t)n0 * 128;
+          segsum_tile<true>(smem + kSmemH, rp_s, nn, tid, ln_s[c2], ln_s[c2 + 1], ln_s[128 + c2], ln_s[128 + c2 + 1],
+                            [&](int v, int col, float s0, float s1) {
+                              *reinterpret_cast<uint32_t*>(agg + (int64_t)v * 128 + col) = pack_bf16x2(s0, s1);
+                            });
         }
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: copy-out + aggregation done (this thread)
       }

@@ -202,5 +202,61 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
+// ---- deterministic segmented sum over a staged tile ---------------------------------------------------
+// Sums the rows of a 128 x 128 bf16 tile image (two T128 tiles at `tile`, generic shared pointer) over the
+// CSR segments of the tile's nodes: node v (local index) owns rows [rp[v], rp[v+1]).  Rows are added in
+// ascending order (= ascending original edge id, the CPU scatter order); no atomics.
+// 128 threads: thread t owns the column pair (2c, 2c+1), c = t & 63, and one half of the node list, so a
+// row costs one 32-bit shared load and ~10 instructions per thread.  kAffine: every element is first mapped
+// to fma(x, scale, bias) (the LayerNorm affine of the message).  flush(v_local, col, sum0, sum1) is called
+// once per node.
+template <bool kAffine, class Flush>
+__device__ __forceinline__ void segsum_tile(const uint8_t* tile, const int* rp, int n_nodes, int t, float sc0,
+                                            float sc1, float bi0, float bi1, Flush flush) {
+  const int c = t & 63, half = t >> 6;
+  const int col = 2 * c;
+  const int nm = n_nodes >> 1;
+  const int vb = half ? nm : 0, ve = half ? n_nodes : nm;
+  if (vb >= ve) return;
+  const uint8_t* base = tile + (col >> 6) * 16384 + (col & 7) * 2;
+  const int chunk = (col & 63) >> 3;
+  uint32_t off8[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) off8[u] = (uint32_t)u * 128u + (uint32_t)((chunk ^ u) << 4);
+  const int jstart = rp[vb], jend = rp[ve];
+  int v = vb;
+  int je = rp[v + 1];
+  float a0 = 0.f, a1 = 0.f;
+  for (int j0 = jstart & ~7; j0 < jend; j0 += 8) {
+    uint32_t w[8];
+    const uint8_t* g = base + j0 * 128;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const uint32_t*>(g + off8[u]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int j = j0 + u;
+      if (j >= jstart && j < jend) {
+        while (j >= je) {  // node v complete (also flushes nodes without rows)
+          flush(v, col, a0, a1);
+          a0 = a1 = 0.f;
+          ++v;
+          je = rp[v + 1];
+        }
+        float x0 = __uint_as_float(w[u] << 16), x1 = __uint_as_float(w[u] & 0xffff0000u);
+        if (kAffine) {
+          x0 = fmaf(x0, sc0, bi0);
+          x1 = fmaf(x1, sc1, bi1);
+        }
+        a0 += x0;
+        a1 += x1;
+      }
+    }
+  }
+  for (; v < ve; ++v) {
+    flush(v, col, a0, a1);
+    a0 = a1 = 0.f;
+  }
+}
+
 }  // namespace tc
 }  // namespace mgn

@@ -10,6 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
 import mgn_oracle as orc  # noqa: E402
+import mgn_oracle_bf16 as ob  # noqa: E402
 
 
 def main():
@@ -38,7 +39,10 @@ def main():
              hidden_layers=2, params=ps, nf=nf, ef=ef, senders=s, receivers=r, target=tgt, mask=mask)
     # gradients are stored as per-tensor norms + a strided sample to keep the fixture small
     specs, P = orc.mlp_specs(cfg)
+    # the same step in the tensor-core mode's arithmetic (bf16 roundings where the kernels store bf16)
+    g_b, loss_b, out_b, _ = ob.step_bf16(cfg, ps, nf, ef, s, r, tgt, mask)
     np.savez(os.path.join(HERE, "cyl_small_golden.npz"), out=out, loss=loss, dnf=dnf,
+             out_bf16=out_b, loss_bf16=loss_b, grad_sample_bf16=g_b[::97].copy(), grad_norm_bf16=np.linalg.norm(g_b),
              grad_sample=g[::97].copy(), grad_norm=np.linalg.norm(g),
              tensor_norms=np.array([np.linalg.norm(g[sp.offset:sp.offset + sp.size]) for sp in specs]))
     # ---- Adam and online normaliser
