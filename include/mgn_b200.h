@@ -143,6 +143,37 @@ int32_t mgn_backward(const mgn_model* m, const mgn_graph* g, const float* d_para
                      float* d_dparams, float* d_dnf, void* d_workspace, size_t workspace_bytes,
                      void* stream);
 
+/* ------------------------------------------------------------------ graph-partitioned meshes (halo exchange) */
+/* A mesh too large for one GPU is split by nodes: a rank owns a set of nodes and every edge whose receiver it owns
+ * (so the scatter-sum stays local and deterministic); sender nodes owned elsewhere are appended to the local node
+ * list as HALO rows.  The model then runs stage by stage, and between stages the caller exchanges halo rows with
+ * the owners (NCCL send/recv, all-to-all, or peer copies - the transport is the caller's):
+ *   forward : ENCODE, [unpack latent(0)], step 0, pack owned rows of latent(1) -> peers unpack into their halo rows,
+ *             step 1, ..., DECODE          (the reference has no counterpart: it is single device, MeshGraphNets.jl:257)
+ *   backward: DECODE, step mps-1, pack+zero the halo rows of the latent gradient -> owners add them, step mps-2, ...,
+ *             ENCODE; the parameter gradient is then summed over ranks.
+ * mgn_forward / mgn_backward are exactly the stage sequences without exchanges. */
+enum { MGN_STAGE_ENCODE = -1, MGN_STAGE_DECODE = -2 }; /* stage >= 0: message-passing step k */
+int32_t mgn_forward_stage(const mgn_model* m, const mgn_graph* g, const float* d_params, const float* d_nf,
+                          const float* d_ef, float* d_out, void* d_workspace, size_t workspace_bytes,
+                          int32_t training, int32_t stage, void* stream);
+/* d_dparams is WRITTEN piecewise: every stage overwrites the gradient of the MLPs it covers. */
+int32_t mgn_backward_stage(const mgn_model* m, const mgn_graph* g, const float* d_params, const float* d_nf,
+                           const float* d_ef, const float* d_dout, float* d_dparams, float* d_dnf,
+                           void* d_workspace, size_t workspace_bytes, int32_t stage, void* stream);
+enum { MGN_HALO_LATENT = 0, /* node latent READ by message-passing step `step` (bf16 rows in bf16 mode, fp32 in fp32 mode) */
+       MGN_HALO_GRAD = 1 }; /* gradient of the node latent (fp32 rows) */
+enum { MGN_ROWS_PACK = 0,      /* buf[i]  = tensor[rows[i]]            */
+       MGN_ROWS_UNPACK = 1,    /* tensor[rows[i]]  = buf[i]            */
+       MGN_ROWS_ADD = 2,       /* tensor[rows[i]] += buf[i]  (fp32; rows must be distinct) */
+       MGN_ROWS_PACK_ZERO = 3  /* pack, then zero the rows             */ };
+/* Bytes of one row of the tensor (latent * 2 or latent * 4). */
+int32_t mgn_halo_row_bytes(const mgn_model* m, int32_t what, size_t* bytes);
+/* d_rows: n_rows local node ids (0-based, device); d_buf: n_rows contiguous rows (device). */
+int32_t mgn_halo_rows(const mgn_model* m, const mgn_graph* g, void* d_workspace, size_t workspace_bytes,
+                      int32_t training, int32_t what, int32_t step, const int32_t* d_rows, int64_t n_rows,
+                      void* d_buf, int32_t op, void* stream);
+
 /* Loss of GraphNetCore.step!(mgn, graph, target, mask, mse_reduce)  <- src/strategies.jl:421:
  * loss = mean(sum_rows((target - out)^2)[mask]); d_mask holds n_mask node ids (the Int32 vector
  * of src/MeshGraphNets.jl:352).  Writes the scalar to d_loss[0] and dloss/dout to d_dout. */

@@ -5,6 +5,7 @@ core.py          host mirror of the GraphNetCore.jl names MeshGraphNets.jl calls
 graph.py         mirror of src/graph.jl      (create_base_graph, build_graph)
 solve.py         mirror of src/solve.jl      (ode_step, ode_func_eval, rollout)
 strategies.py    mirror of src/strategies.jl (DerivativeTraining step)
+partition.py     graph partitioning + halo exchange for meshes larger than one GPU
 parallel.py      data-parallel plumbing (window sharding, gradient / normaliser all-reduce)
 """
 from ._lib import COMPUTE_BF16, COMPUTE_FP32, LIB_PATH, MgnError, load  # noqa: F401
@@ -15,5 +16,9 @@ from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, Normalis
                    triangles_to_edges)
 from .graph import build_graph, create_base_graph  # noqa: F401
 from .parallel import allreduce_mean_, allreduce_normaliser_, shard_windows  # noqa: F401
+from .partition import (DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
+                        masked_mse_partial, partition_bounds, run_partitioned_step)
+from ._lib import (HALO_GRAD, HALO_LATENT, ROWS_ADD, ROWS_PACK, ROWS_PACK_ZERO, ROWS_UNPACK, STAGE_DECODE,  # noqa: F401
+                   STAGE_ENCODE)
 from .solve import ode_func_eval, ode_step, rollout  # noqa: F401
 from .strategies import DerivativeTraining, get_delta, init_train_step, train_step  # noqa: F401

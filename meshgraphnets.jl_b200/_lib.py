@@ -12,6 +12,9 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libmgn_b200.so")
 MGN_OK = 0
 COMPUTE_FP32 = 0
 COMPUTE_BF16 = 1
+STAGE_ENCODE, STAGE_DECODE = -1, -2
+HALO_LATENT, HALO_GRAD = 0, 1
+ROWS_PACK, ROWS_UNPACK, ROWS_ADD, ROWS_PACK_ZERO = 0, 1, 2, 3
 
 
 class MgnError(RuntimeError):
@@ -56,6 +59,10 @@ SIGNATURES = {
     "mgn_workspace_bytes": [_p, _p, _i32, C.POINTER(_sz)],
     "mgn_forward": [_p, _p, _p, _p, _p, _p, _p, _sz, _i32, _p],
     "mgn_backward": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p],
+    "mgn_forward_stage": [_p, _p, _p, _p, _p, _p, _p, _sz, _i32, _i32, _p],
+    "mgn_backward_stage": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _i32, _p],
+    "mgn_halo_row_bytes": [_p, _i32, C.POINTER(_sz)],
+    "mgn_halo_rows": [_p, _p, _p, _sz, _i32, _i32, _i32, _p, _i64, _p, _i32, _p],
     "mgn_loss_mse_masked": [_p, _p, _i64, _i32, _p, _i64, _i32, _p, _p, _p],
     "mgn_adam_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _i64, _p],
     "mgn_adam_step_device": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _p, _p],

@@ -337,6 +337,38 @@ class Model:
     def __call__(self, graph, ps, st=None):
         return self.forward(graph, ps, training=False), st
 
+    # ---- stage-wise execution for graph-partitioned meshes (include/mgn_b200.h, "halo exchange") ----
+    def forward_stage(self, graph: FeatureGraph, ps, stage, training=False, out=None):
+        gi = graph.index
+        ws = self.workspace(gi, training)
+        nf = _dev_f32(graph.node_features, "node_features")
+        ef = _dev_f32(graph.edge_features, "edge_features")
+        if stage == _lib.STAGE_DECODE and out is None:
+            out = torch.empty((nf.shape[0], self.cfg.out_dim), dtype=torch.float32, device=nf.device)
+        call("mgn_forward_stage", self._h, gi._h, _ptr(ps), _ptr(nf), _ptr(ef), _ptr(out), _ptr(ws), ws.numel(),
+             int(training), int(stage), _stream())
+        return out
+
+    def backward_stage(self, graph: FeatureGraph, ps, stage, dps, dout=None, dnf=None):
+        gi = graph.index
+        ws = self.workspace(gi, True)
+        nf = _dev_f32(graph.node_features, "node_features")
+        ef = _dev_f32(graph.edge_features, "edge_features")
+        call("mgn_backward_stage", self._h, gi._h, _ptr(ps), _ptr(nf), _ptr(ef), _ptr(dout), _ptr(dps), _ptr(dnf),
+             _ptr(ws), ws.numel(), int(stage), _stream())
+
+    def halo_row_bytes(self, what):
+        n = C.c_size_t(0)
+        call("mgn_halo_row_bytes", self._h, int(what), C.byref(n))
+        return n.value
+
+    def halo_rows(self, graph: FeatureGraph, training, what, step, rows, buf, op):
+        """rows: int32 CUDA tensor of 0-based local node ids; buf: contiguous CUDA byte buffer."""
+        gi = graph.index
+        ws = self.workspace(gi, training)
+        call("mgn_halo_rows", self._h, gi._h, _ptr(ws), ws.numel(), int(training), int(what), int(step),
+             _ptr(rows), int(rows.numel()), _ptr(buf), int(op), _stream())
+
 
 def init_params(model: Model, seed=1234):
     """Lux default initialisation restated: glorot-uniform Dense weights, zero biases, LayerNorm

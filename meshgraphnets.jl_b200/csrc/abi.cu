@@ -369,6 +369,47 @@ int32_t mgn_backward(const mgn_model* m, const mgn_graph* g, const float* d_para
                   static_cast<cudaStream_t>(stream));
 }
 
+int32_t mgn_forward_stage(const mgn_model* m, const mgn_graph* g, const float* d_params, const float* d_nf,
+                          const float* d_ef, float* d_out, void* d_workspace, size_t workspace_bytes,
+                          int32_t training, int32_t stage, void* stream) {
+  MGN_REQUIRE(m && g && d_params && d_workspace, "forward_stage: null argument");
+  MGN_REQUIRE(stage == MGN_STAGE_ENCODE || stage == MGN_STAGE_DECODE || (stage >= 0 && stage < m->cfg.mps),
+              "forward_stage: bad stage");
+  MGN_REQUIRE(stage != MGN_STAGE_ENCODE || (d_nf && (d_ef || g->E == 0)), "forward_stage: null features");
+  MGN_REQUIRE(stage != MGN_STAGE_DECODE || d_out, "forward_stage: null output");
+  return forward_stage(m, g, d_params, d_nf, d_ef, d_out, d_workspace, workspace_bytes, training != 0, stage,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int32_t mgn_backward_stage(const mgn_model* m, const mgn_graph* g, const float* d_params, const float* d_nf,
+                           const float* d_ef, const float* d_dout, float* d_dparams, float* d_dnf,
+                           void* d_workspace, size_t workspace_bytes, int32_t stage, void* stream) {
+  MGN_REQUIRE(m && g && d_params && d_dparams && d_workspace, "backward_stage: null argument");
+  MGN_REQUIRE(stage == MGN_STAGE_ENCODE || stage == MGN_STAGE_DECODE || (stage >= 0 && stage < m->cfg.mps),
+              "backward_stage: bad stage");
+  MGN_REQUIRE(stage != MGN_STAGE_ENCODE || (d_nf && (d_ef || g->E == 0)), "backward_stage: null features");
+  MGN_REQUIRE(stage != MGN_STAGE_DECODE || d_dout, "backward_stage: null output gradient");
+  return backward_stage(m, g, d_params, d_nf, d_ef, d_dout, d_dparams, d_dnf, d_workspace, workspace_bytes, stage,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int32_t mgn_halo_row_bytes(const mgn_model* m, int32_t what, size_t* bytes) {
+  MGN_REQUIRE(m && bytes, "halo_row_bytes: null argument");
+  MGN_REQUIRE(what == MGN_HALO_LATENT || what == MGN_HALO_GRAD, "halo_row_bytes: unknown tensor");
+  const bool bf16 = m->cfg.compute_mode == MGN_COMPUTE_BF16 && what == MGN_HALO_LATENT;
+  *bytes = (size_t)m->cfg.latent * (bf16 ? 2 : 4);
+  return MGN_OK;
+}
+
+int32_t mgn_halo_rows(const mgn_model* m, const mgn_graph* g, void* d_workspace, size_t workspace_bytes,
+                      int32_t training, int32_t what, int32_t step, const int32_t* d_rows, int64_t n_rows,
+                      void* d_buf, int32_t op, void* stream) {
+  MGN_REQUIRE(m && g && d_workspace, "halo_rows: null argument");
+  MGN_REQUIRE(n_rows >= 0 && (n_rows == 0 || (d_rows && d_buf)), "halo_rows: null rows / buffer");
+  return halo_rows(m, g, d_workspace, workspace_bytes, training != 0, what, step, d_rows, n_rows, d_buf, op,
+                   static_cast<cudaStream_t>(stream));
+}
+
 int32_t mgn_loss_mse_masked(const float* d_out, const float* d_target, int64_t n_nodes,
                             int32_t out_dim, const int32_t* d_mask, int64_t n_mask,
                             int32_t index_base, float* d_loss, float* d_dout, void* stream) {

@@ -176,5 +176,16 @@ int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, con
 int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                  const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
                  size_t ws_bytes, cudaStream_t st);
+int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                      const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
+                      cudaStream_t st);
+int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                       const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                       size_t ws_bytes, int stage, cudaStream_t st);
+int32_t halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
+                  int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st);
+// Row pack / unpack / add between a [N][row_elems] tensor of elem_bytes-wide elements and a contiguous buffer.
+cudaError_t rows_op(void* base, int elem_bytes, int row_elems, const int32_t* rows, int64_t n_rows, int64_t N,
+                    void* buf, int op, cudaStream_t st);
 
 }  // namespace mgn

@@ -177,11 +177,13 @@ int32_t workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training, s
   return MGN_OK;
 }
 
-int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
-                const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
-                cudaStream_t st) {
+constexpr int kStageAll = -3;   // run every stage (mgn_forward / mgn_backward)
+
+int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                      const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
+                      cudaStream_t st) {
   if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
-    return tc_forward(m, g, params, nf, ef, out, ws, ws_bytes, training, st);
+    return tc_forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, stage, st);
   Workspace w;
   layout(m, g, training, ws, w);
   if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_forward");
@@ -189,15 +191,19 @@ int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, con
   const int D = m->cfg.latent, mps = m->cfg.mps;
   const float eps = m->cfg.ln_eps;
   auto saved = [&](size_t i) -> MlpSaved& { return w.saved[training ? i : 0]; };
+  auto lat = [&](int k) { return training ? k : (k & 1); };  // latent buffer read by MP step k
+  const bool all = stage == kStageAll;
 
-  // Encoder.  Raw edge features arrive in original order: gather through perm.
-  MGN_CUDA_TRY(mlp_forward(m->mlps[0], params, op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N,
-                           saved(0), eps, w.nf[0], nullptr, nullptr, nullptr, st));
-  MGN_CUDA_TRY(mlp_forward(m->mlps[1], params, op1(ef, g->perm, m->cfg.edge_in, m->cfg.edge_in), E,
-                           saved(1), eps, w.ef[0], nullptr, nullptr, nullptr, st));
-  int cur = 0;
+  if (all || stage == MGN_STAGE_ENCODE) {
+    // Encoder.  Raw edge features arrive in original order: gather through perm.
+    MGN_CUDA_TRY(mlp_forward(m->mlps[0], params, op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N,
+                             saved(0), eps, w.nf[0], nullptr, nullptr, nullptr, st));
+    MGN_CUDA_TRY(mlp_forward(m->mlps[1], params, op1(ef, g->perm, m->cfg.edge_in, m->cfg.edge_in), E,
+                             saved(1), eps, w.ef[0], nullptr, nullptr, nullptr, st));
+  }
   for (int k = 0; k < mps; ++k) {
-    const int nxt = training ? k + 1 : (cur ^ 1);
+    if (!all && stage != k) continue;
+    const int cur = lat(k), nxt = lat(k + 1);
     float* agg = w.agg[training ? k : 0];
     // edge update (a10) + residual (a12)
     Operand xe{};
@@ -216,32 +222,36 @@ int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, con
     xn.s[1] = {agg, nullptr, D, D};
     MGN_CUDA_TRY(mlp_forward(m->mlps[3 + 2 * k], params, xn, N, saved(3 + 2 * k), eps, nullptr,
                              w.nf[cur], w.nf[nxt], nullptr, st));
-    cur = nxt;
   }
-  // Decoder (a13)
-  const size_t di = m->mlps.size() - 1;
-  MGN_CUDA_TRY(mlp_forward(m->mlps[di], params, op1(w.nf[cur], nullptr, D, D), N, saved(di), eps,
-                           nullptr, nullptr, nullptr, out, st));
+  if (all || stage == MGN_STAGE_DECODE) {  // Decoder (a13)
+    const size_t di = m->mlps.size() - 1;
+    MGN_CUDA_TRY(mlp_forward(m->mlps[di], params, op1(w.nf[lat(mps)], nullptr, D, D), N, saved(di), eps,
+                             nullptr, nullptr, nullptr, out, st));
+  }
   return MGN_OK;
 }
 
-int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
-                 const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                 size_t ws_bytes, cudaStream_t st) {
+int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                       const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                       size_t ws_bytes, int stage, cudaStream_t st) {
   if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
-    return tc_backward(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, st);
+    return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, stage, st);
   Workspace w;
   layout(m, g, true, ws, w);
   if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_backward");
   const int64_t N = g->N, E = g->E;
   const int D = m->cfg.latent, mps = m->cfg.mps;
   const size_t di = m->mlps.size() - 1;
+  const bool all = stage == kStageAll;
 
-  // Decoder: d_nf = d(out)/d(nf[mps])
-  MGN_CUDA_TRY(mlp_backward(m->mlps[di], params, dparams, op1(w.nf[mps], nullptr, D, D), N,
-                            w.saved[di], dout, m->cfg.out_dim, nullptr, 0, nullptr, w, w.d_nf, st));
-  bool d_ef_valid = false;
+  if (all || stage == MGN_STAGE_DECODE) {
+    // Decoder: d_nf = d(out)/d(nf[mps])
+    MGN_CUDA_TRY(mlp_backward(m->mlps[di], params, dparams, op1(w.nf[mps], nullptr, D, D), N,
+                              w.saved[di], dout, m->cfg.out_dim, nullptr, 0, nullptr, w, w.d_nf, st));
+  }
   for (int k = mps - 1; k >= 0; --k) {
+    if (!all && stage != k) continue;
+    const bool d_ef_valid = k != mps - 1;  // the decoder does not read the edge latent
     // node update: nf[k+1] = nf[k] + LN(MLP_n([nf[k]; agg[k]]))
     Operand xn{};
     xn.nseg = 2;
@@ -262,21 +272,55 @@ int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, co
     MGN_CUDA_TRY(node_grad_gather(w.d_nf, w.dxn, 2 * D, w.dxe, g->row_ptr, g->col_ptr, g->csc_slot,
                                   N, D, w.d_nf, st));
     MGN_CUDA_TRY(add_cols(d_ef_valid ? w.d_ef : nullptr, w.dxe, 3 * D, 2 * D, E, D, w.d_ef, st));
-    d_ef_valid = true;
   }
-  // Encoder
-  if (d_ef_valid) {
-    MGN_CUDA_TRY(mlp_backward(m->mlps[1], params, dparams,
-                              op1(ef, g->perm, m->cfg.edge_in, m->cfg.edge_in), E, w.saved[1], w.d_ef,
-                              D, nullptr, 0, nullptr, w, nullptr, st));
+  if (all || stage == MGN_STAGE_ENCODE) {
+    if (mps > 0) {
+      MGN_CUDA_TRY(mlp_backward(m->mlps[1], params, dparams,
+                                op1(ef, g->perm, m->cfg.edge_in, m->cfg.edge_in), E, w.saved[1], w.d_ef,
+                                D, nullptr, 0, nullptr, w, nullptr, st));
+    } else {
+      const MlpLayout& L = m->mlps[1];
+      const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
+      MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
+    }
+    MGN_CUDA_TRY(mlp_backward(m->mlps[0], params, dparams,
+                              op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N, w.saved[0], w.d_nf, D,
+                              nullptr, 0, nullptr, w, dnf, st));
+  }
+  return MGN_OK;
+}
+
+int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
+                cudaStream_t st) {
+  return forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, kStageAll, st);
+}
+
+int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                 const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                 size_t ws_bytes, cudaStream_t st) {
+  return backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st);
+}
+
+// Rows of the node latent / its gradient, for the halo exchange of graph-partitioned meshes.
+int32_t halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
+                  int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st) {
+  if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
+    return tc_halo_rows(m, g, ws, ws_bytes, training, what, step, rows, n_rows, buf, op, st);
+  Workspace w;
+  layout(m, g, training, ws, w);
+  if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_halo_rows");
+  float* base = nullptr;
+  if (what == MGN_HALO_LATENT) {
+    if (step < 0 || step > m->cfg.mps) return fail(MGN_ERR_INVALID, "halo_rows: bad step");
+    base = w.nf[training ? step : (step & 1)];
+  } else if (what == MGN_HALO_GRAD) {
+    if (!training) return fail(MGN_ERR_INVALID, "halo_rows: gradients need a training workspace");
+    base = w.d_nf;
   } else {
-    const MlpLayout& L = m->mlps[1];
-    const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
-    MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
+    return fail(MGN_ERR_INVALID, "halo_rows: unknown tensor");
   }
-  MGN_CUDA_TRY(mlp_backward(m->mlps[0], params, dparams,
-                            op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N, w.saved[0], w.d_nf, D,
-                            nullptr, 0, nullptr, w, dnf, st));
+  MGN_CUDA_TRY(rows_op(base, 4, m->cfg.latent, rows, n_rows, g->N, buf, op, st));
   return MGN_OK;
 }
 

@@ -621,6 +621,30 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   p[i] = p[i] - (mi / c1) / (sqrtf(vi / c2) + eps) * lr;
 }
 
+// One warp per row; rows are copied as 32-bit words (row bytes are a multiple of 4).
+__global__ void __launch_bounds__(256)
+rows_op_kernel(uint32_t* __restrict__ base, int row_words, const int32_t* __restrict__ rows, int64_t n_rows,
+               int64_t N, uint32_t* __restrict__ buf, int op) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n_rows) return;
+  const int64_t r = rows[i];
+  if (r < 0 || r >= N) return;  // ids are validated on the host side of the exchange plan
+  uint32_t* t = base + r * row_words;
+  uint32_t* b = buf + i * row_words;
+  for (int c = threadIdx.x & 31; c < row_words; c += 32) {
+    if (op == MGN_ROWS_PACK) {
+      b[c] = t[c];
+    } else if (op == MGN_ROWS_UNPACK) {
+      t[c] = b[c];
+    } else if (op == MGN_ROWS_ADD) {
+      t[c] = __float_as_uint(__uint_as_float(t[c]) + __uint_as_float(b[c]));
+    } else {
+      b[c] = t[c];
+      t[c] = 0u;
+    }
+  }
+}
+
 OperandDev to_dev(const Operand& x) {
   OperandDev d{};
   d.nseg = x.nseg;
@@ -758,6 +782,17 @@ cudaError_t loss_mse_masked(const float* out, const float* target, int64_t N, in
   ProfScope ps(TAG_LOSS, st);
   zero_kernel<<<blocks_for(N * out_dim, 256), 256, 0, st>>>(dout, N * out_dim);
   loss_kernel<<<1, 1024, 0, st>>>(out, target, out_dim, mask, n_mask, base, loss, dout);
+  return cudaGetLastError();
+}
+
+cudaError_t rows_op(void* base, int elem_bytes, int row_elems, const int32_t* rows, int64_t n_rows, int64_t N,
+                    void* buf, int op, cudaStream_t st) {
+  if (n_rows == 0) return cudaSuccess;
+  if ((row_elems * elem_bytes) % 4 != 0 || op < MGN_ROWS_PACK || op > MGN_ROWS_PACK_ZERO) return cudaErrorInvalidValue;
+  if (op == MGN_ROWS_ADD && elem_bytes != 4) return cudaErrorInvalidValue;
+  ProfScope ps(TAG_TC_MISC, st);
+  rows_op_kernel<<<blocks_for(n_rows, 8), 256, 0, st>>>(static_cast<uint32_t*>(base), row_elems * elem_bytes / 4, rows,
+                                                        n_rows, N, static_cast<uint32_t*>(buf), op);
   return cudaGetLastError();
 }
 

@@ -190,9 +190,11 @@ int32_t tc_backward_scratch_bytes(const mgn_model* m, const mgn_graph* g, size_t
   return MGN_OK;
 }
 
-int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
-                   const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
-                   cudaStream_t st) {
+constexpr int kStageAll = -3;
+
+int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                         const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
+                         cudaStream_t st) {
   if (!g->tiles_ok)
     return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
   TcWorkspace w;
@@ -201,41 +203,44 @@ int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, 
   const int64_t N = g->N, E = g->E;
   const int mps = m->cfg.mps;
   const int node_tiles = (int)((N + kTile - 1) / kTile);
+  const bool all = stage == kStageAll;
 
-  MGN_CUDA_TRY(pack_weights(*m->images, params, w.images, st));
-
-  // Encoder (a9): raw fp32 features -> latent; edge features arrive in original order (perm gather)
-  {
-    FwdParams p{};
-    fill_layers(m, 0, params, w, training, p);
-    p.n_tiles = node_tiles;
-    p.M = N;
-    p.in_mode = IN_RAW;
-    p.raw = nf;
-    p.raw_F = m->cfg.node_in;
-    p.ksteps0 = (m->cfg.node_in + 15) / 16;
-    p.fin_mode = FIN_LN;
-    p.lat_out = w.nf32;
-    p.lat_bf16_out = w.nf16[0];
-    MGN_CUDA_TRY(mlp_forward_tc(p, st));
-  }
-  if (E > 0) {
-    FwdParams p{};
-    fill_layers(m, 1, params, w, training, p);
-    p.n_tiles = g->n_edge_tiles;
-    p.M = E;
-    p.tile_row_start = g->tile_row_start;
-    p.in_mode = IN_RAW;
-    p.raw = ef;
-    p.raw_idx = g->perm;
-    p.raw_F = m->cfg.edge_in;
-    p.ksteps0 = (m->cfg.edge_in + 15) / 16;
-    p.fin_mode = FIN_LN;
-    p.lat_out = w.ef32;
-    p.lat_bf16_out = w.ef16[0];
-    MGN_CUDA_TRY(mlp_forward_tc(p, st));
+  if (all || stage == MGN_STAGE_ENCODE) {
+    MGN_CUDA_TRY(pack_weights(*m->images, params, w.images, st));
+    // Encoder (a9): raw fp32 features -> latent; edge features arrive in original order (perm gather)
+    {
+      FwdParams p{};
+      fill_layers(m, 0, params, w, training, p);
+      p.n_tiles = node_tiles;
+      p.M = N;
+      p.in_mode = IN_RAW;
+      p.raw = nf;
+      p.raw_F = m->cfg.node_in;
+      p.ksteps0 = (m->cfg.node_in + 15) / 16;
+      p.fin_mode = FIN_LN;
+      p.lat_out = w.nf32;
+      p.lat_bf16_out = w.nf16[0];
+      MGN_CUDA_TRY(mlp_forward_tc(p, st));
+    }
+    if (E > 0) {
+      FwdParams p{};
+      fill_layers(m, 1, params, w, training, p);
+      p.n_tiles = g->n_edge_tiles;
+      p.M = E;
+      p.tile_row_start = g->tile_row_start;
+      p.in_mode = IN_RAW;
+      p.raw = ef;
+      p.raw_idx = g->perm;
+      p.raw_F = m->cfg.edge_in;
+      p.ksteps0 = (m->cfg.edge_in + 15) / 16;
+      p.fin_mode = FIN_LN;
+      p.lat_out = w.ef32;
+      p.lat_bf16_out = w.ef16[0];
+      MGN_CUDA_TRY(mlp_forward_tc(p, st));
+    }
   }
   for (int k = 0; k < mps; ++k) {
+    if (!all && stage != k) continue;
     const int cur = training ? k : 0, nxt = training ? k + 1 : 0;
     __nv_bfloat16* agg = w.agg16[training ? k : 0];
     if (E > 0) {  // edge update + residual + aggregation (a10, a11, a12)
@@ -275,7 +280,7 @@ int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, 
       MGN_CUDA_TRY(mlp_forward_tc(p, st));
     }
   }
-  {  // Decoder (a13)
+  if (all || stage == MGN_STAGE_DECODE) {  // Decoder (a13)
     const size_t di = m->mlps.size() - 1;
     FwdParams p{};
     fill_layers(m, di, params, w, training, p);
@@ -289,6 +294,12 @@ int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, 
     MGN_CUDA_TRY(mlp_forward_tc(p, st));
   }
   return MGN_OK;
+}
+
+int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                   const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
+                   cudaStream_t st) {
+  return tc_forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, kStageAll, st);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -390,9 +401,9 @@ int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const floa
 
 }  // namespace
 
-int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
-                    const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
+int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                          const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                          size_t ws_bytes, int stage, cudaStream_t st) {
   if (!g->tiles_ok)
     return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
   TcWorkspace w;
@@ -403,10 +414,11 @@ int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params,
   const int64_t N = g->N, E = g->E;
   const int mps = m->cfg.mps, nd = m->n_dense(), od = m->cfg.out_dim;
   const int node_tiles = (int)((N + kTile - 1) / kTile);
+  const bool all = stage == kStageAll;
   BwdCtx c{m, g, params, dparams, &w, &b, st};
 
-  // ---- Decoder (no LayerNorm): last Dense on CUDA cores, the rest on the tensor cores
-  {
+  if (all || stage == MGN_STAGE_DECODE) {
+    // ---- Decoder (no LayerNorm): last Dense on CUDA cores, the rest on the tensor cores
     const size_t di = m->mlps.size() - 1;
     const MlpLayout& L = m->mlps[di];
     MGN_CUDA_TRY(decoder_head_bwd(dout, od, params + L.w_off[nd - 1], w.saves[di].h[nd - 2], node_tiles, N, b.ztop,
@@ -426,8 +438,9 @@ int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params,
     p.f32_dst[0] = b.d_nf;
     MGN_TRY(run_input(c, di, p));
   }
-  bool d_ef_valid = false;
   for (int k = mps - 1; k >= 0; --k) {
+    if (!all && stage != k) continue;
+    const bool d_ef_valid = k != mps - 1;  // the decoder does not read the edge latent
     {  // node update: nf[k+1] = nf[k] + LN(MLP_n([nf[k]; agg[k]]))
       const size_t mi = 3 + 2 * k;
       MGN_TRY(run_chain(c, mi, false, b.d_nf, nullptr, nullptr));
@@ -469,23 +482,49 @@ int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params,
       p.f32_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p));
       MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.dxs, g->col_ptr, g->csc_slot, N, st));
-      d_ef_valid = true;
     }
   }
-  // ---- Encoders
-  {
+  if (all || stage == MGN_STAGE_ENCODE) {
     const MlpLayout& L = m->mlps[1];
-    if (d_ef_valid) {
+    if (mps > 0 && E > 0) {
       MGN_TRY(run_chain(c, 1, true, b.d_ef, nullptr, nullptr));
       MGN_TRY(run_encoder_input(c, 1, true, ef, g->perm, nullptr));
     } else {
       const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
     }
+    MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr));
+    MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf));
   }
-  MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr));
-  MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf));
   return MGN_OK;
+}
+
+int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
+                    const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
+                    size_t ws_bytes, cudaStream_t st) {
+  return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st);
+}
+
+int32_t tc_halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
+                     int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st) {
+  TcWorkspace w;
+  tc_layout(m, g, training, ws, w);
+  if (what == MGN_HALO_LATENT) {
+    if (step < 0 || step > m->cfg.mps) return fail(MGN_ERR_INVALID, "halo_rows: bad step");
+    if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_halo_rows");
+    if (op == MGN_ROWS_ADD) return fail(MGN_ERR_INVALID, "halo_rows: the bf16 latent cannot be accumulated");
+    MGN_CUDA_TRY(rows_op(w.nf16[training ? step : 0], 2, 128, rows, n_rows, g->N, buf, op, st));
+    return MGN_OK;
+  }
+  if (what == MGN_HALO_GRAD) {
+    if (!training) return fail(MGN_ERR_INVALID, "halo_rows: gradients need a training workspace");
+    BwdScratch b;
+    bwd_layout(m, g, static_cast<char*>(ws) + w.bytes, b);
+    if (w.bytes + b.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_halo_rows");
+    MGN_CUDA_TRY(rows_op(b.d_nf, 4, 128, rows, n_rows, g->N, buf, op, st));
+    return MGN_OK;
+  }
+  return fail(MGN_ERR_INVALID, "halo_rows: unknown tensor");
 }
 
 }  // namespace mgn
