@@ -17,6 +17,7 @@ from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, Normalis
 from .graph import build_graph, create_base_graph  # noqa: F401
 from .parallel import allreduce_mean_, allreduce_normaliser_, shard_windows  # noqa: F401
 from .partition import (DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
+                        build_partition_rank,
                         masked_mse_partial, partition_bounds, run_partitioned_step)
 from ._lib import (HALO_GRAD, HALO_LATENT, ROWS_ADD, ROWS_PACK, ROWS_PACK_ZERO, ROWS_UNPACK, STAGE_DECODE,  # noqa: F401
                    STAGE_ENCODE)

@@ -77,6 +77,41 @@ def build_partition(n_nodes, senders, receivers, world, index_base=1):
     return parts
 
 
+def build_partition_rank(n_nodes, senders, receivers, world, rank, index_base=1):
+    """The LocalGraph of ONE rank (what a process under torchrun needs), without building the others: the send
+    lists follow from the edges whose sender this rank owns and whose receiver a peer owns."""
+    s = np.asarray(senders, np.int64) - index_base
+    r = np.asarray(receivers, np.int64) - index_base
+    b = np.asarray(partition_bounds(n_nodes, world))
+    lo, hi = int(b[rank]), int(b[rank + 1])
+    own_r = (r >= lo) & (r < hi)
+    eid = np.nonzero(own_r)[0]
+    ls, lr = s[eid], r[eid]
+    halo = np.unique(ls[(ls < lo) | (ls >= hi)])
+    halo_owner = np.searchsorted(b[1:], halo, side="right")
+    g = LocalGraph(rank, lo, hi, halo, None, None, eid)
+    pos = np.searchsorted(halo, ls)                              # local id of every sender
+    is_halo = (ls < lo) | (ls >= hi)
+    g.senders = (np.where(is_halo, (hi - lo) + pos, ls - lo) + 1).astype(np.int32)
+    g.receivers = (lr - lo + 1).astype(np.int32)
+    for p in range(world):
+        if p == rank:
+            continue
+        rows = np.nonzero(halo_owner == p)[0]
+        if len(rows):
+            g.recv_rows[p] = ((hi - lo) + rows).astype(np.int32)
+    mine_s = (s >= lo) & (s < hi) & ~own_r                       # my nodes read by edges that live elsewhere
+    dst_owner = np.searchsorted(b[1:], r[mine_s], side="right")
+    src = s[mine_s]
+    for p in range(world):
+        if p == rank:
+            continue
+        need = np.unique(src[dst_owner == p])
+        if len(need):
+            g.send_rows[p] = (need - lo).astype(np.int32)
+    return g
+
+
 class LocalExchange:
     """Transport between P logical ranks living in one process (tests, single-GPU dry runs)."""
 

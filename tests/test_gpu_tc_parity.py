@@ -158,3 +158,31 @@ def test_step_bf16_close_to_bf16_arithmetic_model(pkg, nx, ny, mps, hidden):
     (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
     assert abs(float(loss.cpu()) - loss_b) < 2e-3 * abs(loss_b)
     assert rel(gs.cpu().numpy(), g_b) < 2e-2
+
+
+def test_chain_100k_nodes_bf16_vs_fp32(pkg):
+    """BASELINE configs[3] shape: 1-D chain of 100 000 nodes (src/dataset.jl:379-382 edges through parse_edges,
+    E = 199 998, in-degree <= 2, F_e = 2): the CSR is bit-exact against the oracle and the two compute modes agree
+    within the bf16 tolerance on outputs, loss and gradients (2 MP steps keep the test short)."""
+    n = 100_000
+    rng = np.random.default_rng(9)
+    s, r = orc.parse_edges(orc.create_edges_1d(n))
+    gi = pkg.GraphIndex(n, dev(s), dev(r))
+    rp, perm, _, _ = gi.index_arrays()
+    rp_o, perm_o = orc.build_csr(r, n)
+    assert np.array_equal(rp, rp_o) and np.array_equal(perm, perm_o)
+    cfg = orc.ModelConfig(3, 2, 1, 128, 2, 2)
+    ps = dev((orc.init_params(cfg, seed=2, dtype=np.float64)).astype(np.float32))
+    nf = dev(rng.normal(size=(n, 3)).astype(np.float32))
+    ef = dev(rng.normal(size=(s.shape[0], 2)).astype(np.float32))
+    tgt = dev(rng.normal(size=(n, 1)).astype(np.float32))
+    mask = dev(np.arange(2, n, dtype=np.int32))
+    graph = pkg.FeatureGraph(nf, ef, dev(s), dev(r))
+    res = {}
+    for mode in (pkg.COMPUTE_FP32, pkg.COMPUTE_BF16):
+        model = pkg.Model(3, 2, 1, 2, 128, 2, compute_mode=mode)
+        mgn = pkg.GraphNetwork(model, ps, None, None, None, None)
+        (gs,), loss = pkg.step_(mgn, graph, tgt, mask)
+        res[mode] = (model.forward(graph, ps).cpu().numpy(), float(loss.cpu()), gs.cpu().numpy())
+    a, b = res[pkg.COMPUTE_FP32], res[pkg.COMPUTE_BF16]
+    assert rel(b[0], a[0]) < TOL_OUT and abs(a[1] - b[1]) < TOL_OUT * abs(a[1]) and rel(b[2], a[2]) < TOL_GRAD

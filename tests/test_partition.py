@@ -33,6 +33,12 @@ def test_partition_plan_is_exact(pkg, world):
         for q, rows in p.recv_rows.items():                                  # symmetric plan, same order on both sides
             sent = parts[q].send_rows[p.rank] + parts[q].lo
             assert np.array_equal(sent, p.halo_global[rows - p.n_own])
+        one = pkg.build_partition_rank(N, s, r, world, p.rank)              # the single-rank builder agrees
+        assert np.array_equal(one.senders, p.senders) and np.array_equal(one.receivers, p.receivers)
+        assert np.array_equal(one.halo_global, p.halo_global) and np.array_equal(one.edge_ids, p.edge_ids)
+        assert set(one.send_rows) == set(p.send_rows) and set(one.recv_rows) == set(p.recv_rows)
+        assert all(np.array_equal(one.send_rows[q], p.send_rows[q]) for q in p.send_rows)
+        assert all(np.array_equal(one.recv_rows[q], p.recv_rows[q]) for q in p.recv_rows)
         covered = np.sort(np.concatenate([v for v in p.recv_rows.values()])) if p.recv_rows else np.zeros(0, np.int64)
         assert np.array_equal(covered, np.arange(p.n_own, p.n_local))        # every halo row has exactly one owner
 
