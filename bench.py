@@ -165,7 +165,7 @@ def cpu_reference(batch, seconds, max_steps=None, warmup=1):
         one(warmup + n)
         n += 1
         el = time.perf_counter() - t0
-        if (max_steps and n >= max_steps) or (not max_steps and el >= seconds):
+        if (max_steps and n >= max_steps) or el >= seconds:
             break
     el = time.perf_counter() - t0
     E = s.shape[0]
@@ -173,12 +173,15 @@ def cpu_reference(batch, seconds, max_steps=None, warmup=1):
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (torch-CPU port, all host threads), K
+    timed steps of the batch-1 training step after W warm-ups, capped at ~150 s of wall clock.  Rank 0 only."""
     if rank != 0:
         return
-    edges_s, steps_s, cores, n, el = cpu_reference(1, args.cpu_seconds, max_steps=None, warmup=max(1, min(args.warmup, 2)))
+    edges_s, steps_s, cores, n, el = cpu_reference(1, 150.0, max_steps=max(1, args.steps),
+                                                   warmup=max(1, min(args.warmup, 3)))
     line = {
         "impl": "reference", "metric": METRIC, "value": edges_s, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": n, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1000.0 * el / n, "higher_is_better": True,
+        "steps": n, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1000.0 * el / n, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "train_steps_per_sec": steps_s,
         "config": {"workload": "cylinder_flow_train_step", "nodes": NX * NY, "edges": 10936, "latent": LATENT,

@@ -100,6 +100,7 @@ struct FwdParams {
   __nv_bfloat16* save_xhat;               // image [tile][2 tiles]
   float* save_rstd;                       // [rows]
   unsigned long long* trace;              // debug: per-role %globaltimer stamps of CTA 0 (nullptr = off)
+  uint32_t stagger_ns;                    // start delay unit that de-phases co-resident CTAs (0 = off)
 };
 
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st);

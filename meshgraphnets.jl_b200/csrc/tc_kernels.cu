@@ -13,6 +13,8 @@
 //     CSR segmented sum (a11) from shared memory, so the per-edge message never touches HBM.
 // Two CTAs are resident per SM (<= 113 KB smem, 128 TMEM columns each) so one CTA's epilogue
 // overlaps the other's MMAs.
+#include <cstdlib>
+
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -127,6 +129,12 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
     // ================================ producer ================================
     uint32_t it = 0;
     int tn = 0;
+    // De-phase the two CTAs of an SM (and neighbouring SMs): all CTAs start together, so without a stagger the
+    // whole chip gathers at once and then writes at once, saturating HBM in bursts and idling it in between.
+    if (p.stagger_ns > 0) {
+      const uint32_t slot = (blockIdx.x >= (gridDim.x + 1) / 2 ? 2u : 0u) + (blockIdx.x & 1u);
+      for (uint32_t i = 0; i < slot; ++i) __nanosleep(p.stagger_ns);
+    }
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int64_t row0;
       int cnt;
@@ -472,6 +480,14 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
   ProfScope ps(TAG_TC_MLP_FWD, st);
   FwdParams q = p;
   q.trace = take_trace(0);
+  {
+    static int stagger = -1;
+    if (stagger < 0) {
+      const char* e = getenv("MGN_FWD_STAGGER_NS");
+      stagger = e ? atoi(e) : 0;
+    }
+    q.stagger_ns = grid > n_sm ? (uint32_t)stagger : 0u;
+  }
   mlp_fwd_kernel<<<grid, kThreads, kSmemLaunch, st>>>(q);
   return cudaGetLastError();
 }

@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -65,3 +66,30 @@ def test_no_device_is_an_error_not_a_fallback(pkg):
     h = ctypes.c_void_p()
     st = pkg.load().mgn_graph_create(4, 0, None, None, 1, None, ctypes.byref(h))
     assert st == 2  # MGN_ERR_CUDA: fails loudly, nothing is computed on the CPU
+
+
+def test_product_path_fails_loudly_without_the_library(pkg, monkeypatch, tmp_path):
+    """No CPU / PyTorch fallback: with the shared library missing, loading (and therefore every
+    product call) raises MgnError instead of silently computing somewhere else."""
+    from meshgraphnets_jl_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libmgn_b200.so"))
+    with pytest.raises(_lib.MgnError):
+        _lib.load()
+    with pytest.raises(_lib.MgnError):
+        pkg.one_hot(np.zeros(3, np.int32), 7, 1)
+
+
+def test_device_entry_points_fail_without_a_gpu(pkg):
+    """On a box without a CUDA device the device entry points return MGN_ERR_CUDA (2) - never a fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import ctypes as C
+    lib = pkg.load()
+    n = C.c_int32(-1)
+    assert lib.mgn_device_count(C.byref(n)) == 0 and n.value == 0
+    from meshgraphnets_jl_b200._lib import ModelConfig
+    h = C.c_void_p()
+    st = lib.mgn_model_create(C.byref(ModelConfig(9, 3, 2, 128, 2, 2, 1e-5, 1)), C.byref(h))
+    assert st == 2     # the bf16 model uploads its weight-image plan to the device: MGN_ERR_CUDA
