@@ -168,7 +168,15 @@ class FeatureGraph:
 
     @property
     def index(self):
-        return graph_index_for(self.node_features.shape[0], self.senders, self.receivers, self.index_base)
+        # memoised on the object: the handle (and the workspaces keyed by it) must stay the same between the
+        # forward and backward stages of a step even if the global cache is recycled by other graphs in between
+        key = (self.senders.data_ptr(), self.receivers.data_ptr(), int(self.node_features.shape[0]),
+               int(self.senders.shape[0]), self.index_base)
+        hit = self.__dict__.get("_gi")
+        if hit is None or hit[0] != key:
+            hit = (key, graph_index_for(self.node_features.shape[0], self.senders, self.receivers, self.index_base))
+            self.__dict__["_gi"] = hit
+        return hit[1]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -183,8 +183,9 @@ cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last
 cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const int32_t* raw_idx, int F,
                               const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
                               float* partial, float* d_raw, cudaStream_t st);
-// d_nf[v] += sum over CSC row v of dxs[csc_slot[j]]  (adjoint of the sender gather, deterministic)
-cudaError_t sender_gather_add(float* d_nf, const __nv_bfloat16* dxs, const int32_t* col_ptr,
+// d_nf[v] += recv_sum[v] + sum over CSC row v of dxs[csc_slot[j]]  (adjoints of the receiver and sender gathers;
+// recv_sum is the tile-local segmented sum the input kernel stored; fixed order: deterministic)
+cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs, const int32_t* col_ptr,
                               const int32_t* csc_slot, int64_t N, cudaStream_t st);
 
 }  // namespace tc

@@ -43,14 +43,15 @@ namespace chain {
 constexpr int kThreads = 448;  // warps 0-3 epilogue, 4-11 head (LayerNorm backward), 12 producer, 13 MMA
 constexpr int kHeadThreads = 256;
 constexpr int kWarpP = 12, kWarpM = 13;
-constexpr int kZ = 3, kH = 2, kW = 3;
+// dZ slots: 0-1 hold the head's output (top dZ of a tile; the head may run a whole tile ahead of the MMAs),
+// 2-3 the epilogue's outputs (dZ of the layers below, alternating).  H and W^T images stream through 2-slot rings.
+constexpr int kZ = 4, kH = 2, kW = 2;
 constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemH = kSmemZ + kZ * kImg;
 constexpr uint32_t kSmemW = kSmemH + kH * kImg;
 constexpr uint32_t kSmemScale = kSmemW + kW * kTileB;         // ln scale [128]
 constexpr uint32_t kSmemIdx = kSmemScale + 512;               // gather rows of the tile's dy_b, 128 ints
-constexpr uint32_t kSmemRed = kSmemIdx + 512;                 // [8][3][128] fp32
-constexpr uint32_t kSmemBar = kSmemRed + 8 * 3 * 128 * 4;
+constexpr uint32_t kSmemBar = kSmemIdx + 512;                 // (the head's final [8][3][128] reduction reuses a dZ slot)
 constexpr uint32_t kNumBar = 2 * kZ + 2 * kH + 2 * kW + 4;
 constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
 constexpr uint32_t kSmemTotal = kSmemTmem + 16;
@@ -61,7 +62,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
   float* scale_s = reinterpret_cast<float*>(smem + kSmemScale);
-  float* red_s = reinterpret_cast<float*>(smem + kSmemRed);
   int* idx_s = reinterpret_cast<int*>(smem + kSmemIdx);
   const uint32_t bar0 = s_base + kSmemBar;
   auto z_full = [&](int s) { return bar0 + 8u * s; };
@@ -72,9 +72,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   auto w_empty = [&](int s) { return bar0 + 8u * (2 * kZ + 2 * kH + kW + s); };
   const uint32_t acc_full = bar0 + 8u * (2 * kZ + 2 * kH + 2 * kW);
   const uint32_t acc_empty = acc_full + 8, done_bar = acc_full + 16;
-  // head_go: phase t completes when the MMAs of step 0 of the CTA's t-th tile are done.  The writer of the next
-  // tile's top dZ waits for it, so it never runs more than one use ahead of a Z slot's parity.
-  const uint32_t head_go = acc_full + 24;
   auto z_slot = [&](int s) { return s_base + kSmemZ + (uint32_t)s * kImg; };
   auto h_slot = [&](int s) { return s_base + kSmemH + (uint32_t)s * kImg; };
   auto w_slot = [&](int s) { return s_base + kSmemW + (uint32_t)s * (uint32_t)kTileB; };
@@ -102,7 +99,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     mbar_init(acc_full, 1);
     mbar_init(acc_empty, 128);
     mbar_init(done_bar, 1);
-    mbar_init(head_go, 1);
     fence_mbar_init();
   }
   if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -118,9 +114,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         if (p.head_mode == HEAD_IMAGE) {
-          const uint32_t zc = t_local * (ns + 1), s = zc % kZ;
-          if (t_local > 0) mbar_wait(head_go, (t_local - 1) & 1);
-          mbar_wait(z_empty(s), ((zc / kZ) & 1) ^ 1);
+          const uint32_t s = t_local & 1;
+          mbar_wait(z_empty(s), ((t_local >> 1) & 1) ^ 1);
           mbar_arrive_expect_tx(z_full(s), kImg);
           bulk_g2s(z_slot(s), reinterpret_cast<const uint8_t*>(p.z_top) + (size_t)tile * kImg, kImg, z_full(s));
           mbar_arrive(z_empty(s));  // stands in for the head warps' "column sums done" arrival
@@ -152,9 +147,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       int tn = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         for (int j = 0; j < ns; ++j) {
-          const uint32_t zc = t_local * (ns + 1) + j, zs = zc % kZ;
+          // source dZ of this step: the head's output (j == 0) or the epilogue's output of step j - 1
+          const uint32_t ec = t_local * ns + j - 1;
+          const uint32_t zs = j == 0 ? (t_local & 1) : 2 + (ec & 1);
+          const uint32_t zpar = j == 0 ? ((t_local >> 1) & 1) : ((ec >> 1) & 1);
           trace_ev(p.trace, 1, tn);  // M0: step start
-          mbar_wait(z_full(zs), (zc / kZ) & 1);
+          mbar_wait(z_full(zs), zpar);
           trace_ev(p.trace, 1, tn);  // M1: dZ ready
           if (!first) {  // the epilogue has drained the accumulator of the previous step
             mbar_wait(acc_empty, acc_par);
@@ -186,7 +184,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
                  idesc_mn, (t_local | ks) != 0);
           umma_commit(h_empty(hs));
           umma_commit(z_empty(zs));
-          if (j == 0) umma_commit(head_go);
           ++hc;
         }
       }
@@ -205,13 +202,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
 #pragma unroll 1
       for (int j = 0; j < ns; ++j) {
-        const uint32_t zc = t_local * (ns + 1) + j + 1, zs = zc % kZ, hs = hc % kH;
+        const uint32_t ec = t_local * ns + j, zs = 2 + (ec & 1), hs = hc % kH;
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: step start
         mbar_wait(acc_full, acc_par);
         acc_par ^= 1;
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E1: accumulator full
         mbar_wait(h_full(hs), (hc / kH) & 1);
-        mbar_wait(z_empty(zs), ((zc / kZ) & 1) ^ 1);
+        mbar_wait(z_empty(zs), ((ec >> 1) & 1) ^ 1);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: H there, Z slot free
         tc_fence_after();
 #pragma unroll 1
@@ -306,10 +303,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         int64_t row0;
         int cnt;
         tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
-        const uint32_t zc = t_local * (ns + 1), zs = zc % kZ;
+        const uint32_t zs = t_local & 1;
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L0: tile start
-        if (t_local > 0) mbar_wait(head_go, (t_local - 1) & 1);
-        mbar_wait(z_empty(zs), ((zc / kZ) & 1) ^ 1);
+        mbar_wait(z_empty(zs), ((t_local >> 1) & 1) ^ 1);
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L1: may write
         const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint32_t zb = z_slot(zs) + (cc >> 3) * kTileB;
@@ -327,7 +323,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           float rs[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int i = b0 + rg + 16 * u;
+            const int i = b0 + rg * 4 + u;
             a0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             a1[u] = a0[u];
             c0[u] = a0[u];
@@ -341,9 +337,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
                 a1[u] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
               }
               if (p.dy_b) {
-                const int64_t br = idx_s[i];
-                c0[u] = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8);
-                c1[u] = *reinterpret_cast<const float4*>(p.dy_b + br * 128 + cc * 8 + 4);
+                // consecutive CSR rows share their receiver: reuse the previous row's gather instead of asking L2
+                // again (in-degree d => d-1 of d gathers saved; the max-carveout shared memory leaves no L1)
+                const int br = idx_s[i];
+                if (u > 0 && br == idx_s[i - 1]) {
+                  c0[u] = c0[u - 1];
+                  c1[u] = c1[u - 1];
+                } else {
+                  c0[u] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8);
+                  c1[u] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8 + 4);
+                }
               }
               xq[u] = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
               rs[u] = p.rstd[r];
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int i = b0 + rg + 16 * u;
+            const int i = b0 + rg * 4 + u;
             const float dy[8] = {a0[u].x + c0[u].x, a0[u].y + c0[u].y, a0[u].z + c0[u].z, a0[u].w + c0[u].w,
                                  a1[u].x + c1[u].x, a1[u].y + c1[u].y, a1[u].z + c1[u].z, a1[u].w + c1[u].w};
             const uint32_t xw[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             }
             st_shared_v4(zb + t128_off(i, cc & 7), w[0], w[1], w[2], w[3]);
           }
+          if (lt == 0) trace_ev(p.trace, 0, tn);  // Lb: one batch of rows done
         }
         fence_proxy_async();
         named_bar_sync(2, kHeadThreads);
@@ -398,34 +402,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       }
     }
     // ---- reduce the per-row-group column sums: the two row groups of a warp by shuffle, then [8][3][128] -> [3][128]
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      dbt[e] += __shfl_xor_sync(0xffffffffu, dbt[e], 16);
-      gs[e] += __shfl_xor_sync(0xffffffffu, gs[e], 16);
-      gb[e] += __shfl_xor_sync(0xffffffffu, gb[e], 16);
-    }
-    if ((lt & 16) == 0) {
-      const int wg = lt >> 5;  // head warp 0..7
+    //      through the head slot the next tile would have used (wait until its last reader is done)
+    if (p.head_mode == HEAD_LN) {
+      uint32_t n_local = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) ++n_local;
+      const uint32_t zs = n_local & 1;
+      mbar_wait(z_empty(zs), ((n_local >> 1) & 1) ^ 1);
+      float* red_s = reinterpret_cast<float*>(smem + kSmemZ + zs * kImg);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        red_s[(wg * 3 + 0) * 128 + cc * 8 + e] = dbt[e];
-        red_s[(wg * 3 + 1) * 128 + cc * 8 + e] = gs[e];
-        red_s[(wg * 3 + 2) * 128 + cc * 8 + e] = gb[e];
+        dbt[e] += __shfl_xor_sync(0xffffffffu, dbt[e], 16);
+        gs[e] += __shfl_xor_sync(0xffffffffu, gs[e], 16);
+        gb[e] += __shfl_xor_sync(0xffffffffu, gb[e], 16);
       }
-    }
-    named_bar_sync(2, kHeadThreads);
-    if (lt < 128) {
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      if ((lt & 16) == 0) {
+        const int wg = lt >> 5;  // head warp 0..7
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        t0 += red_s[(g * 3 + 0) * 128 + lt];
-        t1 += red_s[(g * 3 + 1) * 128 + lt];
-        t2 += red_s[(g * 3 + 2) * 128 + lt];
+        for (int e = 0; e < 8; ++e) {
+          red_s[(wg * 3 + 0) * 128 + cc * 8 + e] = dbt[e];
+          red_s[(wg * 3 + 1) * 128 + cc * 8 + e] = gs[e];
+          red_s[(wg * 3 + 2) * 128 + cc * 8 + e] = gb[e];
+        }
       }
-      float* tail = my_partial + (size_t)ns * 16384;
-      tail[lt] = t0;                                 // db of the top layer
-      tail[(size_t)(ns + 1) * 128 + lt] = t1;        // g_scale
-      tail[(size_t)(ns + 1) * 128 + 128 + lt] = t2;  // g_bias
+      named_bar_sync(2, kHeadThreads);
+      if (lt < 128) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          t0 += red_s[(g * 3 + 0) * 128 + lt];
+          t1 += red_s[(g * 3 + 1) * 128 + lt];
+          t2 += red_s[(g * 3 + 2) * 128 + lt];
+        }
+        float* tail = my_partial + (size_t)ns * 16384;
+        tail[lt] = t0;                                 // db of the top layer
+        tail[(size_t)(ns + 1) * 128 + lt] = t1;        // g_scale
+        tail[(size_t)(ns + 1) * 128 + 128 + lt] = t2;  // g_bias
+      }
     }
   }
   tc_fence_before();
@@ -871,6 +883,7 @@ __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16*
 }
 
 __global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restrict__ d_nf,
+                                                                const float* __restrict__ recv_sum,
                                                                 const __nv_bfloat16* __restrict__ dxs,
                                                                 const int32_t* __restrict__ col_ptr,
                                                                 const int32_t* __restrict__ csc_slot, int64_t N) {
@@ -879,6 +892,10 @@ __global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restric
   const int lane = threadIdx.x & 31;
   const int cb = col_ptr[v], ce = col_ptr[v + 1];
   float4 s = *reinterpret_cast<const float4*>(d_nf + v * 128 + lane * 4);
+  if (recv_sum) {
+    const float4 r = *reinterpret_cast<const float4*>(recv_sum + v * 128 + lane * 4);
+    s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w;
+  }
   for (int j = cb; j < ce; ++j) {
     const uint2 q = *reinterpret_cast<const uint2*>(dxs + (int64_t)csc_slot[j] * 128 + lane * 4);
     s.x += bf16_bits_to_float(q.x & 0xffffu);
@@ -990,11 +1007,11 @@ cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const 
   return cudaGetLastError();
 }
 
-cudaError_t sender_gather_add(float* d_nf, const __nv_bfloat16* dxs, const int32_t* col_ptr,
+cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs, const int32_t* col_ptr,
                               const int32_t* csc_slot, int64_t N, cudaStream_t st) {
   if (N == 0) return cudaSuccess;
   ProfScope ps(TAG_NODE_GRAD_GATHER, st);
-  sender_gather_add_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(d_nf, dxs, col_ptr, csc_slot, N);
+  sender_gather_add_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(d_nf, recv_sum, dxs, col_ptr, csc_slot, N);
   return cudaGetLastError();
 }
 

@@ -474,14 +474,13 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.x[2] = w.ef16[k];
       p.sink[0] = SINK_STORE_BF16;  // sender adjoint rows, gathered per node through the CSC below
       p.bf16_dst[0] = b.dxs;
-      p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local
-      p.f32_src[1] = b.d_nf;
-      p.f32_dst[1] = b.d_nf;
+      p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores into the buffer that
+      p.f32_dst[1] = b.d_agg;       // held d_agg (consumed by the chain kernel above), added to d_nf by the gather below
       p.sink[2] = SINK_ADD_F32;     // edge-latent residual
       p.f32_src[2] = d_ef_valid ? b.d_ef : nullptr;
       p.f32_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p));
-      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.dxs, g->col_ptr, g->csc_slot, N, st));
+      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_slot, N, st));
     }
   }
   if (all || stage == MGN_STAGE_ENCODE) {

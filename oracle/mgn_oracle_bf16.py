@@ -171,9 +171,9 @@ def step_bf16(cfg: orc.ModelConfig, params, nf, ef, senders, receivers, target, 
         dy = d_agg[rc_] if d_ef is None else f32(d_ef + d_agg[rc_])
         z0 = me.chain(g, me.head_ln(g, dy), L - 1)
         dx = me.input_dx(g, z0)
-        d_nf = _seg_sum(dx[:, 128:256], range(E), rc_, N, init=d_nf)
+        recv = _seg_sum(dx[:, 128:256], range(E), rc_, N)       # tile-local segmented sum, stored ...
         d_ef = f32(dx[:, 256:]) if d_ef is None else f32(d_ef + dx[:, 256:])
-        d_nf = _seg_sum(dx[:, :128], csc, sc_, N, init=d_nf)
+        d_nf = _seg_sum(dx[:, :128], csc, sc_, N, init=f32(d_nf + recv))   # ... then added with the sender rows
     d_raw = None
     for enc, dy, raw in ((enc_e, d_ef, np.asarray(ef)[perm]), (enc_n, d_nf, nf)):
         if dy is None:
