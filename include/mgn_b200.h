@@ -206,7 +206,8 @@ int32_t mgn_profile_tag_name(int32_t tag, char* buf, size_t n);
 /* NormaliserOnline state on the device: d_state = [acc_sum[F] | acc_sum_sq[F] | acc_count |
  * num_acc] (2F+2 floats).  mgn_norm_online_update is the accumulate branch of the callable
  * (src/graph.jl:80,84,93; src/strategies.jl:399-410); it is skipped on-device once
- * num_acc >= max_acc.  d_x is [M][F]. */
+ * num_acc >= max_acc.  d_x is [M][F], F <= 64.  Deterministic two-stage sum; the first call on a device allocates a
+ * 64 KB scratch (do it once outside CUDA-graph capture); updates on one device must not run concurrently. */
 int32_t mgn_norm_online_update(const float* d_x, int64_t rows, int32_t features, float* d_state,
                                float max_acc, void* stream);
 /* y = (x - mean)/std (inverse == 0) or y = x*std + mean (inverse != 0, inverse_data at

@@ -8,6 +8,8 @@
 //   scatter(+)   sequential sum in ascending edge id             SURVEY 8 a11 (here: CSR segment)
 //   step! loss   mean(sum_rows((target-out)^2)[mask])            src/strategies.jl:421
 //   Adam         Optimisers.update                               src/MeshGraphNets.jl:374-378
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mgn {
@@ -532,31 +534,54 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g,
 // ---------------------------------------------------------------------------------------------
 // Normalisers
 // ---------------------------------------------------------------------------------------------
-// state = [sum[F] | sumsq[F] | count | num_acc]; single block => fixed summation order.
-__global__ void __launch_bounds__(1024)
-norm_update_kernel(const float* __restrict__ x, int64_t rows, int F, float* __restrict__ state,
-                   float max_acc) {
-  __shared__ float red[32];
-  if (state[2 * F + 1] >= max_acc) return;  // uniform across the block
-  for (int f = 0; f < F; ++f) {
-    for (int which = 0; which < 2; ++which) {
-      float s = 0.f;
-      for (int64_t r = threadIdx.x; r < rows; r += blockDim.x) {
-        const float v = x[r * F + f];
-        s += which ? v * v : v;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      __syncthreads();
-      if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-      __syncthreads();
-      if (threadIdx.x < 32) {
-        float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) state[which * F + f] += t;
-      }
+// state = [sum[F] | sumsq[F] | count | num_acc].  Two stages, both with a fixed summation order (deterministic):
+// every block reduces a fixed, contiguous range of rows to 2F partial sums; one block then adds the partials in
+// block order and updates the state.  F <= 64.
+constexpr int kNormBlocks = 128;
+constexpr int kNormMaxF = 64;
+__global__ void __launch_bounds__(256)
+norm_partial_kernel(const float* __restrict__ x, int64_t rows, int F, const float* __restrict__ state, float max_acc,
+                    float* __restrict__ partial) {
+  __shared__ float red[8][2 * kNormMaxF];
+  if (state[2 * F + 1] >= max_acc) return;  // uniform
+  const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // thread t walks the flattened [rows][F] range with stride 256: element e belongs to feature e % F
+  for (int f0 = 0; f0 < F; f0 += 1) {
+    float s = 0.f, q = 0.f;
+    for (int64_t r = r0 + threadIdx.x; r < r1; r += 256) {
+      const float v = x[r * F + f0];
+      s += v;
+      q = fmaf(v, v, q);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      red[warp][f0] = s;
+      red[warp][F + f0] = q;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * F) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    partial[(int64_t)blockIdx.x * 2 * kNormMaxF + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+norm_finish_kernel(const float* __restrict__ partial, int nblk, int64_t rows, int F, float* __restrict__ state,
+                   float max_acc) {
+  if (state[2 * F + 1] >= max_acc) return;
+  if (threadIdx.x < 2 * F) {
+    float t = 0.f;
+    for (int b = 0; b < nblk; ++b) t += partial[(int64_t)b * 2 * kNormMaxF + threadIdx.x];
+    state[threadIdx.x] += t;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -818,8 +843,22 @@ cudaError_t adam_step_device(float* p, const float* g, float* m, float* v, int64
 
 cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
                                cudaStream_t st) {
+  if (F > kNormMaxF) return cudaErrorInvalidValue;
+  // per-device scratch for the block partials, allocated on first use (outside any stream capture: callers warm up
+  // before capturing).  One normaliser update at a time per device - the reference is single-stream.
+  static float* scratch[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (!scratch[dev]) {
+    cudaError_t e = cudaMalloc(&scratch[dev], sizeof(float) * kNormBlocks * 2 * kNormMaxF);
+    if (e != cudaSuccess) return e;
+  }
+  const int nblk = (int)std::min<int64_t>(kNormBlocks, std::max<int64_t>(1, (rows + 2047) / 2048));
   { ProfScope ps(TAG_NORM, st);
-  norm_update_kernel<<<1, 1024, 0, st>>>(x, rows, F, state, max_acc); }
+  norm_partial_kernel<<<nblk, 256, 0, st>>>(x, rows, F, state, max_acc, scratch[dev]); }
+  { ProfScope ps(TAG_NORM, st);
+  norm_finish_kernel<<<1, 128, 0, st>>>(scratch[dev], nblk, rows, F, state, max_acc); }
   return cudaGetLastError();
 }
 
