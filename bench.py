@@ -135,6 +135,12 @@ def cpu_reference(batch, seconds, max_steps=None, warmup=1):
     same CylinderFlow-shaped workload.  Returns (edges/s, steps/s, cores, n_timed)."""
     import mgn_oracle as orc
     import torch_cpu_ref as tref
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would make the baseline
+    # single threaded)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     data, vel, nt, N = make_workload(batch)
     cells = data["cells"][0]
     s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
