@@ -300,7 +300,11 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
           // tile-local CSR row pointer -> shared memory (read by the aggregation after two more barriers)
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
           if (tid <= nn) rp_s[tid] = p.row_ptr[n0 + tid] - (int)row0;
-          if (tid == 0 && nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
+          if (tid == 0) {
+            if (nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
+            rp_s[130] = n0;
+            rp_s[131] = nn;
+          }
         }
         // residual rows of the first copy-out batch: issued now so that their latency hides behind the LayerNorm
         float4 r0[8], r1[8];
@@ -321,27 +325,24 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         };
         if (last) issue_residual(0);
         float mean = 0.f, rstd = 1.f;
-        if (last) {  // LayerNorm statistics: two extra passes over TMEM (cheap), biased variance
-          float s = 0.f;
+        if (last) {  // LayerNorm statistics in ONE extra pass over TMEM: sums of the data shifted by the row's first
+                     // element (the shifted-data formula keeps the fp32 variance accurate), biased variance
+          float s = 0.f, q = 0.f, shift = 0.f;
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             float v[32];
             tmem_ld32(t_lane + c * 32, v);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) s += v[j] + bias_s[l * 128 + c * 32 + j];
-          }
-          mean = s * (1.f / 128.f);
-          float q = 0.f;
-#pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            float v[32];
-            tmem_ld32(t_lane + c * 32, v);
+            if (c == 0) shift = v[0] + bias_s[l * 128];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float d = v[j] + bias_s[l * 128 + c * 32 + j] - mean;
+              const float d = v[j] + bias_s[l * 128 + c * 32 + j] - shift;
+              s += d;
               q = fmaf(d, d, q);
             }
           }
+          const float ms = s * (1.f / 128.f);
+          mean = shift + ms;
+          q = fmaxf(q * (1.f / 128.f) - ms * ms, 0.f) * 128.f;
           rstd = 1.f / sqrtf(q * (1.f / 128.f) + p.eps);
           if (p.save_rstd && row < cnt) p.save_rstd[row0 + row] = rstd;
         }
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         //      ascending CSR slot = ascending original edge id (the CPU scatter order, a11).  The column is
         //      read 8 rows at a time (loads in flight together); the adds stay strictly sequential.
         if (p.fin_mode == FIN_LN_RESID_AGG) {
-          const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
+          const int n0 = rp_s[130], nn = rp_s[131];
           const int c2 = 2 * (tid & 63);
           __nv_bfloat16* agg = p.agg_bf16 + (int64_t)n0 * 128;
           segsum_tile<true>(smem + kSmemH, rp_s, nn, tid, ln_s[c2], ln_s[c2 + 1], ln_s[128 + c2], ln_s[128 + c2 + 1],

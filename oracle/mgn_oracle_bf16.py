@@ -60,10 +60,23 @@ class _Mlp:
                 self.h.append(a)
         if self.s.ln is None:
             return z
-        mean = f32(z.sum(axis=1, keepdims=True) / 128.0)
-        var = f32(((z - mean) ** 2).sum(axis=1, keepdims=True) / 128.0)
-        self.rstd = f32(1.0 / np.sqrt(f32(var + self.eps)))
-        self.xhat = q((z - mean) * self.rstd)
+        # LayerNorm statistics exactly as the kernel computes them: one pass, data shifted by the row's first
+        # element, sequential fp32 sums (fused multiply-add for the squares), biased variance
+        f = np.float32
+        z32 = z.astype(f)
+        shift = z32[:, :1]
+        d = (z32 - shift).astype(f)
+        ssum = np.zeros(z32.shape[0], f)
+        qsum = np.zeros(z32.shape[0], f)
+        for j in range(z32.shape[1]):
+            ssum = (ssum + d[:, j]).astype(f)
+            qsum = (d[:, j].astype(np.float64) * d[:, j] + qsum).astype(f)
+        ms = (ssum * f(1.0 / 128.0)).astype(f)
+        mean32 = (shift[:, 0] + ms).astype(f)
+        var128 = (np.maximum((qsum * f(1.0 / 128.0)).astype(f) - (ms * ms).astype(f), f(0)) * f(128)).astype(f)
+        rstd32 = (f(1) / np.sqrt(((var128 * f(1.0 / 128.0)).astype(f) + self.eps).astype(f))).astype(f)
+        self.rstd = rstd32.astype(np.float64)[:, None]
+        self.xhat = q(((z32 - mean32[:, None]).astype(f) * rstd32[:, None]).astype(f))
         sc = self.p[self.s.ln[1]:self.s.ln[1] + 128]
         bi = self.p[self.s.ln[0]:self.s.ln[0] + 128]
         return f32(self.xhat * sc + bi)
