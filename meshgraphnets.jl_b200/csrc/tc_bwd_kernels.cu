@@ -702,14 +702,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
           const bool in_place = p.f32_src[b] != nullptr;
           float* dst = p.f32_dst[b] + (int64_t)n0 * 128;
-          segsum_tile<false>(smem + kSmemStage, rp_s, nn, tid, 1.f, 1.f, 0.f, 0.f,
-                             [&](int v, int col, float s0, float s1) {
-                               float* d = dst + (int64_t)v * 128 + col;
+          segsum_tile<false>(s_stage, s_base + kSmemRp, nn, tid, nullptr, nullptr,
+                             [&](int v, int col0, const float (&a)[8]) {
+                               float* d = dst + (int64_t)v * 128 + col0;
                                if (in_place) {
-                                 atomicAdd(d, s0);
-                                 atomicAdd(d + 1, s1);
+#pragma unroll
+                                 for (int e = 0; e < 8; ++e) atomicAdd(d + e, a[e]);
                                } else {
-                                 *reinterpret_cast<float2*>(d) = make_float2(s0, s1);
+                                 *reinterpret_cast<float4*>(d) = make_float4(a[0], a[1], a[2], a[3]);
+                                 *reinterpret_cast<float4*>(d + 4) = make_float4(a[4], a[5], a[6], a[7]);
                                }
                              });
         }

@@ -307,23 +307,23 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
           }
         }
         // residual rows of the first copy-out batch: issued now so that their latency hides behind the LayerNorm
+        // residual rows are fetched 4 per thread at a time into one half of r0/r1 while the other half is consumed
         float4 r0[8], r1[8];
         const int cc = tid & 15, rg = tid >> 4;
         const bool resid = p.fin_mode != FIN_LN;
-        auto issue_residual = [&](int b0) {
+        auto issue_residual = [&](int k, int h) {  // batch k covers rows 32k + rg + 8u
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int i = b0 + rg + 8 * u;
-            r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[u] = r0[u];
+          for (int u = 0; u < 4; ++u) {
+            const int i = 32 * k + rg + 8 * u;
+            r0[4 * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r1[4 * h + u] = r0[4 * h + u];
             if (resid && i < cnt) {
               const int64_t o = (row0 + i) * 128 + cc * 8;
-              r0[u] = *reinterpret_cast<const float4*>(p.lat_in + o);
-              r1[u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+              r0[4 * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o);
+              r1[4 * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
             }
           }
         };
-        if (last) issue_residual(0);
         float mean = 0.f, rstd = 1.f;
         if (last) {  // LayerNorm statistics in ONE extra pass over TMEM: sums of the data shifted by the row's first
                      // element (the shifted-data formula keeps the fp32 variance accurate), biased variance
@@ -393,9 +393,29 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
           bulk_commit();
           store_pending = true;
         }
-        // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced).
-        //      Rows are handled 8 at a time per thread so that all residual loads of a batch are in flight
-        //      together (2 memory round trips per tile instead of 16).
+        // ---- first residual batch in flight, then the deterministic segmented sum of the (pre-residual) messages
+        //      (rows in ascending CSR slot = ascending original edge id, the CPU scatter order, a11).  The
+        //      aggregation is shared-memory bound, so it runs BEFORE the copy-out's burst of global stores fills
+        //      the SM's memory pipeline.
+        if (tid == 0) trace_ev(p.trace, 0, tn);  // C0: xhat bulk store issued
+        issue_residual(0, 0);
+        if (tid == 0) trace_ev(p.trace, 0, tn);  // C1: first residual batch issued
+        if (p.fin_mode == FIN_LN_RESID_AGG) {
+          const int n0 = rp_s[130], nn = rp_s[131];
+          __nv_bfloat16* agg = p.agg_bf16 + (int64_t)n0 * 128;
+          segsum_tile<true>(s_h, s_base + kSmemRp, nn, tid, ln_s, ln_s + 128,
+                            [&](int v, int col0, const float (&a)[8]) {
+                              uint4 o;
+                              o.x = pack_bf16x2(a[0], a[1]);
+                              o.y = pack_bf16x2(a[2], a[3]);
+                              o.z = pack_bf16x2(a[4], a[5]);
+                              o.w = pack_bf16x2(a[6], a[7]);
+                              *reinterpret_cast<uint4*>(agg + (int64_t)v * 128 + col0) = o;
+                            });
+        }
+        if (tid == 0) trace_ev(p.trace, 0, tn);  // C: aggregation done
+        // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced), four batches of
+        //      32 rows, the residual rows of batch k+1 in flight while batch k is written
         {
           float sc[8], bi[8];
 #pragma unroll
@@ -403,24 +423,26 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
             sc[j] = ln_s[cc * 8 + j];
             bi[j] = ln_s[128 + cc * 8 + j];
           }
-#pragma unroll 1
-          for (int b0 = 0; b0 < kTile; b0 += 64) {
-            if (b0 != 0) issue_residual(b0);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = b0 + rg + 8 * u;
+          for (int k = 0; k < 4; ++k) {
+            const int h = k & 1;
+            if (k + 1 < 4) issue_residual(k + 1, h ^ 1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int i = 32 * k + rg + 8 * u;
               if (i >= cnt) continue;
               const uint4 xq = ld_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7));
               const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
               float m[8];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
-                m[2 * j] = fmaf(__low2float(h), sc[2 * j], bi[2 * j]);
-                m[2 * j + 1] = fmaf(__high2float(h), sc[2 * j + 1], bi[2 * j + 1]);
+                const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
+                m[2 * j] = fmaf(__low2float(hh), sc[2 * j], bi[2 * j]);
+                m[2 * j + 1] = fmaf(__high2float(hh), sc[2 * j + 1], bi[2 * j + 1]);
               }
-              m[0] += r0[u].x; m[1] += r0[u].y; m[2] += r0[u].z; m[3] += r0[u].w;
-              m[4] += r1[u].x; m[5] += r1[u].y; m[6] += r1[u].z; m[7] += r1[u].w;
+              const float4 a0 = r0[4 * h + u], a1 = r1[4 * h + u];
+              m[0] += a0.x; m[1] += a0.y; m[2] += a0.z; m[3] += a0.w;
+              m[4] += a1.x; m[5] += a1.y; m[6] += a1.z; m[7] += a1.w;
               const int64_t o = (row0 + i) * 128 + cc * 8;
               *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
               *reinterpret_cast<float4*>(p.lat_out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
@@ -431,20 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
               bq.w = pack_bf16x2(m[6], m[7]);
               *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
             }
-            if (tid == 0) trace_ev(p.trace, 0, tn);  // C: one copy-out batch done
           }
-        }
-        // ---- deterministic segmented sum of the (pre-residual) messages: thread == column, rows in
-        //      ascending CSR slot = ascending original edge id (the CPU scatter order, a11).  The column is
-        //      read 8 rows at a time (loads in flight together); the adds stay strictly sequential.
-        if (p.fin_mode == FIN_LN_RESID_AGG) {
-          const int n0 = rp_s[130], nn = rp_s[131];
-          const int c2 = 2 * (tid & 63);
-          __nv_bfloat16* agg = p.agg_bf16 + (int64_t)n0 * 128;
-          segsum_tile<true>(smem + kSmemH, rp_s, nn, tid, ln_s[c2], ln_s[c2 + 1], ln_s[128 + c2], ln_s[128 + c2 + 1],
-                            [&](int v, int col, float s0, float s1) {
-                              *reinterpret_cast<uint32_t*>(agg + (int64_t)v * 128 + col) = pack_bf16x2(s0, s1);
-                            });
         }
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: copy-out + aggregation done (this thread)
       }

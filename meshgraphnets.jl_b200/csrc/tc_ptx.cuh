@@ -203,58 +203,68 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
 }
 
 // ---- deterministic segmented sum over a staged tile ---------------------------------------------------
-// Sums the rows of a 128 x 128 bf16 tile image (two T128 tiles at `tile`, generic shared pointer) over the
-// CSR segments of the tile's nodes: node v (local index) owns rows [rp[v], rp[v+1]).  Rows are added in
-// ascending order (= ascending original edge id, the CPU scatter order); no atomics.
-// 128 threads: thread t owns the column pair (2c, 2c+1), c = t & 63, and one half of the node list, so a
-// row costs one 32-bit shared load and ~10 instructions per thread.  kAffine: every element is first mapped
-// to fma(x, scale, bias) (the LayerNorm affine of the message).  flush(v_local, col, sum0, sum1) is called
-// once per node.
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// Sums the rows of a 128 x 128 bf16 tile image (two T128 tiles at shared address `tile`) over the CSR segments
+// of the tile's nodes: node v (local index) owns rows [rp[v], rp[v+1]) (rp at shared address `rp`).  Rows are
+// added in ascending order (= ascending original edge id, the CPU scatter order); no atomics.
+// 128 threads: thread t owns one 16-byte chunk of columns (8 columns: chunk t & 7 of tile (t >> 3) & 1) and one
+// eighth of the node list, so a row costs ONE 128-bit shared load per thread (quarter-warps read 128 contiguous
+// bytes: conflict-free) - the shared-memory pipe is shared with the co-resident CTA's global traffic, so the
+// number of memory instructions, not the arithmetic, is what this loop pays for.  Node-major: up to 4 rows of
+// a node are in flight together, then added in order.  kAffine: every element is first mapped to
+// fma(x, scale, bias) (the LayerNorm affine of the message; sc / bi at shared float pointers).
+// flush(v_local, col0, sums[8]) once per node.
 template <bool kAffine, class Flush>
-__device__ __forceinline__ void segsum_tile(const uint8_t* tile, const int* rp, int n_nodes, int t, float sc0,
-                                            float sc1, float bi0, float bi1, Flush flush) {
-  const int c = t & 63, half = t >> 6;
-  const int col = 2 * c;
-  const int nm = n_nodes >> 1;
-  const int vb = half ? nm : 0, ve = half ? n_nodes : nm;
-  if (vb >= ve) return;
-  const uint8_t* base = tile + (col >> 6) * 16384 + (col & 7) * 2;
-  const int chunk = (col & 63) >> 3;
-  uint32_t off8[8];
+__device__ __forceinline__ void segsum_tile(uint32_t tile, uint32_t rp, int n_nodes, int t, const float* sc_s,
+                                            const float* bi_s, Flush flush) {
+  const uint32_t chunk = (uint32_t)t & 7u, tsel = ((uint32_t)t >> 3) & 1u;
+  const int grp = t >> 4;
+  const int vb = (n_nodes * grp) >> 3, ve = (n_nodes * (grp + 1)) >> 3;
+  const int col0 = (int)(tsel * 64u + chunk * 8u);
+  const uint32_t base = tile + tsel * 16384u;
+  float sc[8], bi[8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) off8[u] = (uint32_t)u * 128u + (uint32_t)((chunk ^ u) << 4);
-  const int jstart = rp[vb], jend = rp[ve];
-  int v = vb;
-  int je = rp[v + 1];
-  float a0 = 0.f, a1 = 0.f;
-  for (int j0 = jstart & ~7; j0 < jend; j0 += 8) {
-    uint32_t w[8];
-    const uint8_t* g = base + j0 * 128;
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = kAffine ? sc_s[col0 + e] : 1.f;
+    bi[e] = kAffine ? bi_s[col0 + e] : 0.f;
+  }
+  int jb = vb < ve ? (int)ld_shared_u32(rp + 4u * vb) : 0;
+  for (int v = vb; v < ve; ++v) {
+    const int je = (int)ld_shared_u32(rp + 4u * (v + 1));
+    float a[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const uint32_t*>(g + off8[u]);
+    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    for (int j0 = jb; j0 < je; j0 += 4) {
+      uint4 q[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int j = j0 + u;
-      if (j >= jstart && j < jend) {
-        while (j >= je) {  // node v complete (also flushes nodes without rows)
-          flush(v, col, a0, a1);
-          a0 = a1 = 0.f;
-          ++v;
-          je = rp[v + 1];
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t j = (uint32_t)(j0 + u);
+        q[u] = make_uint4(0u, 0u, 0u, 0u);
+        if ((int)j < je) q[u] = ld_shared_v4(base + j * 128u + ((chunk ^ (j & 7u)) << 4));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < je) {
+          const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0 = __uint_as_float(w[e] << 16), x1 = __uint_as_float(w[e] & 0xffff0000u);
+            if (kAffine) {
+              x0 = fmaf(x0, sc[2 * e], bi[2 * e]);
+              x1 = fmaf(x1, sc[2 * e + 1], bi[2 * e + 1]);
+            }
+            a[2 * e] += x0;
+            a[2 * e + 1] += x1;
+          }
         }
-        float x0 = __uint_as_float(w[u] << 16), x1 = __uint_as_float(w[u] & 0xffff0000u);
-        if (kAffine) {
-          x0 = fmaf(x0, sc0, bi0);
-          x1 = fmaf(x1, sc1, bi1);
-        }
-        a0 += x0;
-        a1 += x1;
       }
     }
-  }
-  for (; v < ve; ++v) {
-    flush(v, col, a0, a1);
-    a0 = a1 = 0.f;
+    flush(v, col0, a);
+    jb = je;
   }
 }
 
