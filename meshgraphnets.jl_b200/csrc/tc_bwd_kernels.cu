@@ -195,7 +195,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t hc = 0, t_local = 0, acc_par = 0;
     int tn = 0;
-    float db[kMaxSteps] = {0.f, 0.f, 0.f};
+    // bias-gradient partials: this thread sums 8 columns (one 16-byte chunk) over one eighth of the rows, per step
+    float db0[8], db1[8], db2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) db0[e] = db1[e] = db2[e] = 0.f;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
       int64_t row0;
       int cnt;
@@ -245,21 +248,31 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             bulk_commit();
           }
         }
-        // bias gradient: column sums of the bf16 dZ just written (thread == column; 8 loads in flight)
+        // bias gradient: column sums of the bf16 dZ just written.  128-bit shared loads (16 per thread instead of
+        // 128 narrow ones: the shared-memory pipe is the scarce resource); rows >= cnt hold zeros.
         {
-          const int col = tid;
-          const uint8_t* cptr = smem + kSmemZ + zs * kImg + (col >> 6) * kTileB + (col & 7) * 2;
-          const int chunk = (col & 63) >> 3;
-          float s = 0.f;
-          for (int r0 = 0; r0 < cnt; r0 += 8) {
-            float x[8];
+          const uint32_t chunk = (uint32_t)tid & 7u, tsel = ((uint32_t)tid >> 3) & 1u, grp = (uint32_t)tid >> 4;
+          const uint32_t zb2 = z_slot(zs) + tsel * (uint32_t)kTileB;
+          float t8[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u)   // rows >= cnt hold zeros
-              x[u] = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(cptr + t128_off(min(r0 + u, kTile - 1), chunk)));
+          for (int e = 0; e < 8; ++e) t8[e] = 0.f;
+#pragma unroll 4
+          for (uint32_t rr = 0; rr < 16; ++rr) {
+            const uint32_t jr = grp * 16u + rr;
+            const uint4 q = ld_shared_v4(zb2 + jr * 128u + ((chunk ^ (jr & 7u)) << 4));
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int u = 0; u < 8; ++u) s += (r0 + u < cnt) ? x[u] : 0.f;
+            for (int e = 0; e < 4; ++e) {
+              t8[2 * e] += __uint_as_float(w[e] << 16);
+              t8[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+            }
           }
-          db[j] += s;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (j == 0) db0[e] += t8[e];
+            else if (j == 1) db1[e] += t8[e];
+            else db2[e] += t8[e];
+          }
         }
         named_bar_sync(1, 128);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E4: column sums done
@@ -285,7 +298,26 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 #pragma unroll
         for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
-      my_partial[(size_t)ns * 16384 + (size_t)(j + 1) * 128 + tid] = db[j];
+    }
+    // bias gradients: [8 row groups][3 steps][128] through an epilogue dZ slot (all MMAs and the last dZ bulk
+    // store are done), then a fixed-order sum over the row groups
+    named_bar_sync(1, 128);
+    {
+      float* red = reinterpret_cast<float*>(smem + kSmemZ + 2 * kImg);
+      const int col0 = (int)((((uint32_t)tid >> 3) & 1u) * 64u + ((uint32_t)tid & 7u) * 8u), grp = tid >> 4;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        red[(grp * 3 + 0) * 128 + col0 + e] = db0[e];
+        red[(grp * 3 + 1) * 128 + col0 + e] = db1[e];
+        red[(grp * 3 + 2) * 128 + col0 + e] = db2[e];
+      }
+      named_bar_sync(1, 128);
+      for (int j = 0; j < ns; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += red[(g * 3 + j) * 128 + tid];
+        my_partial[(size_t)ns * 16384 + (size_t)(j + 1) * 128 + tid] = t;
+      }
     }
     if (tid == 0) bulk_wait0();
   } else {
