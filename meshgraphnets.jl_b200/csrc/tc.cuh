@@ -74,6 +74,7 @@ struct FwdParams {
   // input operand
   int in_mode;
   const __nv_bfloat16 *x0, *x1, *x2;  // row-major [rows][128] bf16
+  const __nv_bfloat16* x2_img;        // IN_GATHER3: the third segment as tile images [tile][2][16 KB] (bulk copies)
   const int32_t *idx0, *idx1;         // IN_GATHER3: rows of x0 for K-blocks {0,1} / {2,3}
   const float* raw;                   // IN_RAW: fp32 [rows][raw_F]
   const int32_t* raw_idx;             // IN_RAW: optional row gather (CSR perm)
@@ -91,7 +92,8 @@ struct FwdParams {
   int fin_mode;
   const float* lat_in;                // fp32 [rows][128] residual input
   float* lat_out;                     // fp32 [rows][128]
-  __nv_bfloat16* lat_bf16_out;        // bf16 shadow of lat_out
+  __nv_bfloat16* lat_bf16_out;        // bf16 shadow of lat_out (row-major) ...
+  __nv_bfloat16* lat_img_out;         // ... or, when non-null, as tile images (one 32 KB bulk store per tile)
   __nv_bfloat16* agg_bf16;            // [nodes][128]
   float* out;                         // FIN_LINEAR: [rows][out_dim]
   int out_dim;
@@ -156,7 +158,8 @@ struct InputParams {
   const int32_t* row_ptr;
   const __nv_bfloat16* dz0;            // image
   int nblk;                            // 1..3
-  const __nv_bfloat16* x[3];           // block b source, row-major [*][128]
+  const __nv_bfloat16* x[3];           // block b source, row-major [*][128] ...
+  int x_is_img[3];                     // ... or tile images [tile][2][16 KB] (identity rows; one bulk copy per tile)
   const int32_t* idx[3];               // optional row gather
   const __nv_bfloat16* wt_img;         // W_0^T image: tile (nb, kb) at (nb * 2 + kb) * 16 KB
   int sink[3];

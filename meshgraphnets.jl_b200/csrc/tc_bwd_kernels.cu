@@ -577,6 +577,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         const __nv_bfloat16* src_base = p.x[b];
         const int32_t* idx = p.idx[b];
         const uint32_t dst = x_slot(xs);
+        if (p.x_is_img[b]) {  // the tile's own rows, stored as a tile image: one bulk copy
+          if (lane == 0) {
+            mbar_arrive_expect_tx(x_full(xs), kImg);
+            bulk_g2s(dst, reinterpret_cast<const uint8_t*>(src_base) + (size_t)tile * kImg, kImg, x_full(xs));
+          } else {
+            mbar_arrive(x_full(xs));
+          }
+          if (lane == 0) trace_ev(p.trace, 3, tn);  // P2: image copy issued
+          ++xc;
+          continue;
+        }
         int64_t srow[4];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {  // the 4 index loads of this lane are in flight together

@@ -180,6 +180,15 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
               }
               fence_proxy_async();
               mbar_arrive(full_bar(s));
+            } else if (p.in_mode == IN_GATHER3 && (kb >> 1) == 2 && p.x2_img != nullptr) {
+              // the tile's own rows of the third segment are stored as a tile image: one bulk copy per K-block
+              if (lane == 0) {
+                mbar_arrive_expect_tx(full_bar(s), (uint32_t)kTileB);
+                bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.x2_img) + (size_t)tile * 2 * kTileB + (size_t)(kb & 1) * kTileB,
+                         (uint32_t)kTileB, full_bar(s));
+              } else {
+                mbar_arrive(full_bar(s));
+              }
             } else {
               const __nv_bfloat16* src_base;
               const int seg = kb >> 1;
@@ -414,6 +423,16 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
                             });
         }
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C: aggregation done
+        const bool img_out = p.lat_img_out != nullptr;
+        if (img_out) {
+          // the bf16 shadow of the new latent overwrites the xhat tile in place (same thread, same 16 bytes) and leaves as
+          // one bulk store: every reader of xhat (aggregation, the xhat save) must be done first
+          if (tid == 0 && store_pending) {
+            bulk_wait_read0();
+            store_pending = false;
+          }
+          named_bar_sync(1, 128);
+        }
         // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced), four batches of
         //      32 rows, the residual rows of batch k+1 in flight while batch k is written
         {
@@ -430,7 +449,10 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int i = 32 * k + rg + 8 * u;
-              if (i >= cnt) continue;
+              if (i >= cnt) {
+                if (img_out) st_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7), 0u, 0u, 0u, 0u);
+                continue;
+              }
               const uint4 xq = ld_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7));
               const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
               float m[8];
@@ -451,8 +473,18 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
               bq.y = pack_bf16x2(m[2], m[3]);
               bq.z = pack_bf16x2(m[4], m[5]);
               bq.w = pack_bf16x2(m[6], m[7]);
-              *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
+              if (img_out) st_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7), bq.x, bq.y, bq.z, bq.w);
+              else *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
             }
+          }
+        }
+        if (img_out) {
+          fence_proxy_async();
+          named_bar_sync(1, 128);
+          if (tid == 0) {
+            bulk_s2g(reinterpret_cast<uint8_t*>(p.lat_img_out) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
+            bulk_commit();
+            store_pending = true;
           }
         }
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: copy-out + aggregation done (this thread)

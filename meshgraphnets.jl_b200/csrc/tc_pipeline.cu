@@ -3,7 +3,8 @@
 // Data layout in HBM (all owned by the caller's workspace):
 //   images      bf16 weight images, 16 KB 128B-swizzled K-major tiles (repacked every forward)
 //   nf32 / ef32 fp32 master copies of the node / edge latents, row-major [rows][128]
-//   nf16 / ef16 bf16 shadows used as GEMM operands / gather sources, one per MP step when training
+//   nf16 / ef16 bf16 shadows used as GEMM operands / gather sources, one per MP step when training; nf16 is row-major
+//               (gathered by index), ef16 is stored as tile images (a tile only ever reads its own rows: bulk copies)
 //   agg16       bf16 aggregated messages per MP step
 //   saves       per MLP: hidden activations and LayerNorm xhat as tile images [tile][2][16 KB]
 //               (written and read back with 1-D bulk copies), rstd fp32 [rows]
@@ -63,7 +64,7 @@ void tc_layout(const mgn_model* m, const mgn_graph* g, bool training, void* base
   w.ef16.resize(nlat);
   for (int k = 0; k < nlat; ++k) {
     w.nf16[k] = b.h((size_t)N * 128);
-    w.ef16[k] = b.h((size_t)std::max<int64_t>(E, 1) * 128);
+    w.ef16[k] = static_cast<__nv_bfloat16*>(b.raw((size_t)std::max<int64_t>(edge_tiles, 1) * 2 * kTileB));  // tile images
   }
   w.agg16.resize(training ? std::max(mps, 1) : 1);
   for (auto& a : w.agg16) a = b.h((size_t)N * 128);
@@ -235,7 +236,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.ksteps0 = (m->cfg.edge_in + 15) / 16;
       p.fin_mode = FIN_LN;
       p.lat_out = w.ef32;
-      p.lat_bf16_out = w.ef16[0];
+      p.lat_img_out = w.ef16[0];
       MGN_CUDA_TRY(mlp_forward_tc(p, st));
     }
   }
@@ -253,13 +254,13 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.row_ptr = g->row_ptr;
       p.in_mode = IN_GATHER3;
       p.x0 = w.nf16[cur];
-      p.x2 = w.ef16[cur];
+      p.x2_img = w.ef16[cur];
       p.idx0 = g->send_csr;
       p.idx1 = g->recv_csr;
       p.fin_mode = FIN_LN_RESID_AGG;
       p.lat_in = w.ef32;
       p.lat_out = w.ef32;
-      p.lat_bf16_out = w.ef16[nxt];
+      p.lat_img_out = w.ef16[nxt];
       p.agg_bf16 = agg;
       MGN_CUDA_TRY(mlp_forward_tc(p, st));
     } else {
@@ -472,6 +473,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.x[1] = w.nf16[k];
       p.idx[1] = g->recv_csr;
       p.x[2] = w.ef16[k];
+      p.x_is_img[2] = 1;
       p.sink[0] = SINK_STORE_BF16;  // sender adjoint rows, gathered per node through the CSC below
       p.bf16_dst[0] = b.dxs;
       p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores into the buffer that
