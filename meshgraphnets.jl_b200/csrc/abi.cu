@@ -242,6 +242,7 @@ int32_t mgn_graph_destroy(mgn_graph* g) {
   cudaFree(g->perm_sender);
   cudaFree(g->csc_slot);
   cudaFree(g->tile_row_start);
+  cudaFree(g->csc_pos);
   cudaFree(g->tile_node_start);
   delete g;
   return MGN_OK;

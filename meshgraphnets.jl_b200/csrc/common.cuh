@@ -87,6 +87,7 @@ struct mgn_graph {
   int32_t* tile_row_start = nullptr;   // [n_edge_tiles + 1]
   int32_t* tile_node_start = nullptr;  // [n_edge_tiles + 1]
   int32_t n_edge_tiles = 0;
+  int32_t* csc_pos = nullptr;          // [E] CSC slot -> row of the same edge in tile-image space: tile * 128 + row in tile
   bool tiles_ok = false;               // false when a node has more than 128 in-edges
 };
 

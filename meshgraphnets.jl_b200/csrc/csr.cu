@@ -243,6 +243,19 @@ int32_t build_graph_index(mgn_graph* g, const int32_t* d_senders, const int32_t*
     MGN_CUDA_TRY(cudaMalloc(&g->tile_node_start, sizeof(int32_t) * tnode.size()));
     MGN_CUDA_TRY(cudaMemcpy(g->tile_row_start, trow.data(), sizeof(int32_t) * trow.size(), cudaMemcpyHostToDevice));
     MGN_CUDA_TRY(cudaMemcpy(g->tile_node_start, tnode.data(), sizeof(int32_t) * tnode.size(), cudaMemcpyHostToDevice));
+    // CSC slot -> row in tile-image space (tensors stored as [tile][128 rows] images are gathered through this)
+    if (E > 0) {
+      std::vector<int32_t> slot((size_t)E), pos((size_t)E), tile_of((size_t)E);
+      MGN_CUDA_TRY(cudaMemcpy(slot.data(), g->csc_slot, sizeof(int32_t) * E, cudaMemcpyDeviceToHost));
+      for (size_t t = 0; t + 1 < trow.size(); ++t)
+        for (int32_t j = trow[t]; j < trow[t + 1]; ++j) tile_of[(size_t)j] = (int32_t)t;
+      for (int64_t j = 0; j < E; ++j) {
+        const int32_t sl = slot[(size_t)j], t = tile_of[(size_t)sl];
+        pos[(size_t)j] = t * 128 + (sl - trow[(size_t)t]);
+      }
+      MGN_CUDA_TRY(cudaMalloc(&g->csc_pos, sizeof(int32_t) * E));
+      MGN_CUDA_TRY(cudaMemcpy(g->csc_pos, pos.data(), sizeof(int32_t) * E, cudaMemcpyHostToDevice));
+    }
   }
   return MGN_OK;
 }

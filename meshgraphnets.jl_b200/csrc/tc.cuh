@@ -149,7 +149,8 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
 
 // Input kernel: first Dense layer of an MLP whose input is made of 128-wide bf16 blocks.
 //   dW_0[block b] += X_b^T dZ_0 ; dX_b = dZ_0 W_0[block b]^T -> sink b
-enum SinkMode { SINK_NONE = 0, SINK_STORE_BF16 = 1, SINK_ADD_F32 = 2, SINK_SEGSUM_F32 = 3 };
+enum SinkMode { SINK_NONE = 0, SINK_STORE_BF16 = 1, SINK_ADD_F32 = 2, SINK_SEGSUM_F32 = 3,
+                SINK_STORE_IMG = 4 /* bf16 tile image [tile][2][16 KB]: one bulk store of the staged tile */ };
 struct InputParams {
   int n_tiles;
   int64_t M;
@@ -188,8 +189,9 @@ cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const 
                               float* partial, float* d_raw, cudaStream_t st);
 // d_nf[v] += recv_sum[v] + sum over CSC row v of dxs[csc_slot[j]]  (adjoints of the receiver and sender gathers;
 // recv_sum is the tile-local segmented sum the input kernel stored; fixed order: deterministic)
-cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs, const int32_t* col_ptr,
-                              const int32_t* csc_slot, int64_t N, cudaStream_t st);
+// dxs is a tile-image tensor; csc_pos maps a CSC entry to its row in image space (tile * 128 + row in tile).
+cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs_img, const int32_t* col_ptr,
+                              const int32_t* csc_pos, int64_t N, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace mgn

@@ -661,6 +661,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
     uint32_t acc_par = 0;
     int tn = 0;
+    bool stage_store_pending = false;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int64_t row0;
       int cnt;
@@ -672,6 +673,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         acc_par ^= 1;
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E1: accumulator full
         tc_fence_after();
+        if (tid == 0 && stage_store_pending) {  // a bulk store of the staged tile must have read it
+          bulk_wait_read0();
+          stage_store_pending = false;
+        }
         named_bar_sync(1, 128);  // the previous copy-out has finished reading the staging tile
         if (p.sink[b] == SINK_SEGSUM_F32) {  // tile-local CSR row pointer (visible after the next barrier)
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
@@ -691,10 +696,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         }
         tc_fence_before();
         mbar_arrive(acc_empty);
+        if (p.sink[b] == SINK_STORE_IMG) fence_proxy_async();
         named_bar_sync(1, 128);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: staged
         const int sink = p.sink[b];
-        if (sink == SINK_STORE_BF16) {
+        if (sink == SINK_STORE_IMG) {
+          // the staged tile already has the image layout (rows >= cnt are zero): it leaves as one bulk store
+          if (tid == 0) {
+            bulk_s2g(reinterpret_cast<uint8_t*>(p.bf16_dst[b]) + (size_t)tile * kImg, s_stage, kImg);
+            bulk_commit();
+            stage_store_pending = true;
+          }
+        } else if (sink == SINK_STORE_BF16) {
           const int cc = tid & 15, rg = tid >> 4;
 #pragma unroll 4
           for (int i = rg; i < cnt; i += 8) {
@@ -760,6 +773,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: sink done (this thread)
       }
     }
+    if (tid == 0 && stage_store_pending) bulk_wait0();
     mbar_wait(done_bar, 0);
     tc_fence_after();
     for (int b = 0; b < nblk; ++b) {
@@ -928,9 +942,9 @@ __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16*
 
 __global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restrict__ d_nf,
                                                                 const float* __restrict__ recv_sum,
-                                                                const __nv_bfloat16* __restrict__ dxs,
+                                                                const __nv_bfloat16* __restrict__ dxs_img,
                                                                 const int32_t* __restrict__ col_ptr,
-                                                                const int32_t* __restrict__ csc_slot, int64_t N) {
+                                                                const int32_t* __restrict__ csc_pos, int64_t N) {
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= N) return;
   const int lane = threadIdx.x & 31;
@@ -940,8 +954,13 @@ __global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restric
     const float4 r = *reinterpret_cast<const float4*>(recv_sum + v * 128 + lane * 4);
     s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w;
   }
+  // lane owns columns 4*lane .. 4*lane+3: half (lane & 1) of the 16-byte chunk (lane >> 1) & 7 of tile lane >> 4
+  const uint32_t tsel = (uint32_t)lane >> 4, chunk = ((uint32_t)lane >> 1) & 7u, half = (uint32_t)lane & 1u;
+  const uint8_t* img = reinterpret_cast<const uint8_t*>(dxs_img);
   for (int j = cb; j < ce; ++j) {
-    const uint2 q = *reinterpret_cast<const uint2*>(dxs + (int64_t)csc_slot[j] * 128 + lane * 4);
+    const uint32_t pos = (uint32_t)csc_pos[j], t = pos >> 7, r = pos & 127u;
+    const uint2 q = *reinterpret_cast<const uint2*>(img + (size_t)t * kImg + tsel * (uint32_t)kTileB + t128_off((int)r, (int)chunk) +
+                                                    half * 8u);
     s.x += bf16_bits_to_float(q.x & 0xffffu);
     s.y += __uint_as_float(q.x & 0xffff0000u);
     s.z += bf16_bits_to_float(q.y & 0xffffu);
@@ -1051,11 +1070,11 @@ cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const 
   return cudaGetLastError();
 }
 
-cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs, const int32_t* col_ptr,
-                              const int32_t* csc_slot, int64_t N, cudaStream_t st) {
+cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs_img, const int32_t* col_ptr,
+                              const int32_t* csc_pos, int64_t N, cudaStream_t st) {
   if (N == 0) return cudaSuccess;
   ProfScope ps(TAG_NODE_GRAD_GATHER, st);
-  sender_gather_add_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(d_nf, recv_sum, dxs, col_ptr, csc_slot, N);
+  sender_gather_add_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(d_nf, recv_sum, dxs_img, col_ptr, csc_pos, N);
   return cudaGetLastError();
 }
 

@@ -106,7 +106,7 @@ void fill_layers(const mgn_model* m, size_t mi, const float* params, const TcWor
 // Scratch of the backward pass, placed after the forward workspace.
 struct BwdScratch {
   float *d_nf = nullptr, *d_ef = nullptr, *d_agg = nullptr;  // fp32 gradients of the latents
-  __nv_bfloat16* dxs = nullptr;                              // [E][128] sender adjoint rows (CSR order)
+  __nv_bfloat16* dxs = nullptr;                              // sender adjoint rows as tile images [edge tile][2][16 KB]
   __nv_bfloat16 *dz0 = nullptr, *ztop = nullptr;             // tile images
   float* partial = nullptr;                                  // per-CTA / per-tile weight-gradient partials
   size_t partial_floats = 0;
@@ -121,7 +121,7 @@ void bwd_layout(const mgn_model* m, const mgn_graph* g, void* base, BwdScratch& 
   b.d_nf = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
   b.d_ef = bump.f((size_t)std::max<int64_t>(E, 1) * 128);
   b.d_agg = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
-  b.dxs = bump.h((size_t)std::max<int64_t>(E, 1) * 128);
+  b.dxs = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(edge_tiles, 1) * 2 * kTileB));  // tile images
   b.dz0 = static_cast<__nv_bfloat16*>(bump.raw((size_t)max_tiles * 2 * kTileB));
   b.ztop = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(node_tiles, 1) * 2 * kTileB));
   const int grid = backward_grid((int)max_tiles);
@@ -474,7 +474,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.idx[1] = g->recv_csr;
       p.x[2] = w.ef16[k];
       p.x_is_img[2] = 1;
-      p.sink[0] = SINK_STORE_BF16;  // sender adjoint rows, gathered per node through the CSC below
+      p.sink[0] = SINK_STORE_IMG;   // sender adjoint rows (tile image), gathered per node through the CSC below
       p.bf16_dst[0] = b.dxs;
       p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores into the buffer that
       p.f32_dst[1] = b.d_agg;       // held d_agg (consumed by the chain kernel above), added to d_nf by the gather below
@@ -482,7 +482,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.f32_src[2] = d_ef_valid ? b.d_ef : nullptr;
       p.f32_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p));
-      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_slot, N, st));
+      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st));
     }
   }
   if (all || stage == MGN_STAGE_ENCODE) {
