@@ -669,6 +669,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
 #pragma unroll 1
       for (int b = 0; b < nblk; ++b) {
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: block start
+        // SINK_ADD_F32 with a source: the tile's fp32 rows (16 per thread) are requested NOW, before the wait for the
+        // accumulator and the staging pass, so that their latency is off the critical path (1 CTA/SM: registers abound)
+        float4 pr0[16], pr1[16];
+        const bool prefetch = p.sink[b] == SINK_ADD_F32 && p.f32_src[b] != nullptr;
+        if (prefetch) {
+          const int pcc = tid & 15, prg = tid >> 4;
+          const float* src = p.f32_src[b];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int i = prg + 8 * u;
+            pr0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            pr1[u] = pr0[u];
+            if (i < cnt) {
+              const int64_t o = (row0 + i) * 128 + pcc * 8;
+              pr0[u] = *reinterpret_cast<const float4*>(src + o);
+              pr1[u] = *reinterpret_cast<const float4*>(src + o + 4);
+            }
+          }
+        }
         mbar_wait(acc_full, acc_par);
         acc_par ^= 1;
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E1: accumulator full
@@ -715,41 +734,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
             *reinterpret_cast<uint4*>(p.bf16_dst[b] + (row0 + i) * 128 + cc * 8) = q;
           }
         } else if (sink == SINK_ADD_F32) {
-          // dst = src + dX, 8 rows per thread in flight (2 memory round trips per tile)
+          // dst = src + dX; the source rows were prefetched at the top of the block
           const int cc = tid & 15, rg = tid >> 4;
-          const float* src = p.f32_src[b];
-#pragma unroll 1
-          for (int b0 = 0; b0 < kTile; b0 += 64) {
-            float4 r0[8], r1[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = b0 + rg + 8 * u;
-              r0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-              r1[u] = r0[u];
-              if (src && i < cnt) {
-                const int64_t o = (row0 + i) * 128 + cc * 8;
-                r0[u] = *reinterpret_cast<const float4*>(src + o);
-                r1[u] = *reinterpret_cast<const float4*>(src + o + 4);
-              }
+          for (int u = 0; u < 16; ++u) {
+            const int i = rg + 8 * u;
+            if (i >= cnt) continue;
+            const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
+            const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+            float m[8];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              m[2 * e] = bf16_bits_to_float(qw[e] & 0xffffu);
+              m[2 * e + 1] = __uint_as_float(qw[e] & 0xffff0000u);
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int i = b0 + rg + 8 * u;
-              if (i >= cnt) continue;
-              const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
-              const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
-              float m[8];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                m[2 * e] = bf16_bits_to_float(qw[e] & 0xffffu);
-                m[2 * e + 1] = __uint_as_float(qw[e] & 0xffff0000u);
-              }
-              const int64_t o = (row0 + i) * 128 + cc * 8;
-              *reinterpret_cast<float4*>(p.f32_dst[b] + o) =
-                  make_float4(m[0] + r0[u].x, m[1] + r0[u].y, m[2] + r0[u].z, m[3] + r0[u].w);
-              *reinterpret_cast<float4*>(p.f32_dst[b] + o + 4) =
-                  make_float4(m[4] + r1[u].x, m[5] + r1[u].y, m[6] + r1[u].z, m[7] + r1[u].w);
+            float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+            if (prefetch) {
+              a0 = pr0[u];
+              a1 = pr1[u];
             }
+            const int64_t o = (row0 + i) * 128 + cc * 8;
+            *reinterpret_cast<float4*>(p.f32_dst[b] + o) = make_float4(m[0] + a0.x, m[1] + a0.y, m[2] + a0.z, m[3] + a0.w);
+            *reinterpret_cast<float4*>(p.f32_dst[b] + o + 4) = make_float4(m[4] + a1.x, m[5] + a1.y, m[6] + a1.z, m[7] + a1.w);
           }
         } else if (sink == SINK_SEGSUM_F32) {
           // adjoint of the receiver gather: deterministic segmented sum over the tile's CSR rows.  In place
