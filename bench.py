@@ -62,9 +62,10 @@ def parse():
 # synthetic workload (shared by both arms)
 # ---------------------------------------------------------------------------------------------
 def make_workload(batch, seed=1234):
-    import mgn_oracle as orc
-    pos, cells, nt = orc.cylinder_flow_mesh(NX, NY)
-    vel = orc.synthetic_velocity(pos, T_FRAMES + 1, seed=seed)
+    import mgn_pkg                         # product-side generators: the GPU arm never touches oracle/
+    wl = mgn_pkg.pkg
+    pos, cells, nt = wl.cylinder_flow_mesh(NX, NY)
+    vel = wl.synthetic_velocity(pos, T_FRAMES + 1, seed=seed)
     N = pos.shape[0]
     # `batch` time windows of one trajectory share the topology: block-diagonal graph
     data = {"node_type": np.tile(nt, batch).reshape(1, -1, 1),
@@ -218,8 +219,7 @@ def measure(args, rank, world, local_rank, B, steps, warmup, extras):
     mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOnline(3, dev),
                            {"velocity": pkg.NormaliserOnline(2, dev), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
                            {"velocity": pkg.NormaliserOnline(2, dev)})
-    import mgn_oracle as orc
-    mask = torch.from_numpy(orc.node_mask(data_h["node_type"].reshape(-1), [0, 5])).to(dev)
+    mask = torch.from_numpy(pkg.node_mask(data_h["node_type"].reshape(-1), [0, 5])).to(dev)
     opt = pkg.Adam(1e-4)
     opt_state = opt.setup(mgn.ps)
     strat = pkg.DerivativeTraining()

@@ -6,6 +6,7 @@ graph.py         mirror of src/graph.jl      (create_base_graph, build_graph)
 solve.py         mirror of src/solve.jl      (ode_step, ode_func_eval, rollout)
 strategies.py    mirror of src/strategies.jl (DerivativeTraining step)
 partition.py     graph partitioning + halo exchange for meshes larger than one GPU
+workloads.py     synthetic BASELINE workloads + the driver's mask helpers (src/MeshGraphNets.jl:352-358)
 parallel.py      data-parallel plumbing (window sharding, gradient / normaliser all-reduce)
 """
 from ._lib import COMPUTE_BF16, COMPUTE_FP32, LIB_PATH, MgnError, load  # noqa: F401
@@ -22,4 +23,6 @@ from .partition import (DistExchange, LocalExchange, LocalGraph, PartitionedMode
 from ._lib import (HALO_GRAD, HALO_LATENT, ROWS_ADD, ROWS_PACK, ROWS_PACK_ZERO, ROWS_UNPACK, STAGE_DECODE,  # noqa: F401
                    STAGE_ENCODE)
 from .solve import ode_func_eval, ode_step, rollout  # noqa: F401
+from .workloads import (chain_edges, cylinder_flow_mesh, node_mask, synthetic_velocity, tet_grid_edges,  # noqa: F401
+                        val_mask)
 from .strategies import DerivativeTraining, get_delta, init_train_step, train_step  # noqa: F401

@@ -103,3 +103,19 @@ def test_normalisers_oracle():
     assert np.allclose(mm(np.array([[3.0]])), 0.5) and np.allclose(mm.inverse(np.array([[0.5]])), 3.0)
     ms = orc.NormaliserOfflineMeanStd(1.0, 2.0)
     assert np.allclose(ms(np.array([[5.0]])), 2.0) and np.allclose(ms.inverse(np.array([[2.0]])), 5.0)
+
+
+def test_product_workload_generators_match_the_oracle(pkg):
+    """bench.py / tools build their inputs with the product-side generators (meshgraphnets.jl_b200/workloads.py);
+    they must be the same workloads the oracle defines."""
+    import mgn_oracle as orc
+    for a, b in zip(pkg.cylinder_flow_mesh(65, 29), orc.cylinder_flow_mesh(65, 29)):
+        assert np.array_equal(a, b)
+    pos, _, nt = orc.cylinder_flow_mesh(9, 7)
+    assert np.array_equal(pkg.synthetic_velocity(pos, 5, seed=3), orc.synthetic_velocity(pos, 5, seed=3))
+    assert np.array_equal(pkg.node_mask(nt, [0, 5]), orc.node_mask(nt, [0, 5]))
+    assert np.array_equal(pkg.val_mask(nt, [0, 5], 2), orc.val_mask(nt, [0, 5], 2))
+    assert np.array_equal(pkg.chain_edges(17), orc.create_edges_1d(17))
+    e = pkg.tet_grid_edges(5)
+    assert e.shape == (3 * 5 * 5 * 4 + 3 * 5 * 4 * 4 + 4 ** 3, 2) and (e[:, 0] < e[:, 1]).all()
+    assert np.array_equal(e, np.unique(e, axis=0))          # sorted, unique

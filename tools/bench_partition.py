@@ -18,25 +18,10 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+sys.path[:0] = [ROOT]
 import mgn_pkg  # noqa: E402
 
 pkg = mgn_pkg.pkg
-
-
-def tet_grid_edges(n):
-    """Unique undirected edges of the Kuhn subdivision of an n^3 node grid, 1-based, lexicographically sorted
-    [U, 2] (the format src/dataset.jl:345 hands to parse_edges): 3 axis, 3 face-diagonal and 1 body-diagonal
-    neighbour per node."""
-    idx = np.arange(n ** 3, dtype=np.int64).reshape(n, n, n)
-    out = []
-    for dx, dy, dz in ((0, 0, 1), (0, 1, 0), (1, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0), (1, 1, 1)):
-        a = idx[:n - dx, :n - dy, :n - dz].reshape(-1)
-        b = idx[dx:, dy:, dz:].reshape(-1)
-        out.append(np.stack([a, b], 1))
-    e = np.concatenate(out)
-    e = e[np.lexsort((e[:, 1], e[:, 0]))]
-    return (e + 1).astype(np.int32)
 
 
 def main():
@@ -57,7 +42,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = args.grid
     N = n ** 3
-    s, r = pkg.parse_edges(tet_grid_edges(n))
+    s, r = pkg.parse_edges(pkg.tet_grid_edges(n))
     E = int(s.shape[0])
     part = pkg.build_partition_rank(N, s, r, world, rank)
     del s, r

@@ -13,8 +13,7 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
-import mgn_oracle as orc  # noqa: E402
+sys.path[:0] = [ROOT]
 import mgn_pkg  # noqa: E402
 
 pkg = mgn_pkg.pkg
@@ -23,9 +22,9 @@ pkg = mgn_pkg.pkg
 def main():
     mode = pkg.COMPUTE_BF16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else pkg.COMPUTE_FP32
     dev = torch.device("cuda", 0)
-    pos, cells, nt = orc.cylinder_flow_mesh(65, 29)
+    pos, cells, nt = pkg.cylinder_flow_mesh(65, 29)
     T = 51
-    vel = orc.synthetic_velocity(pos, T, seed=1)
+    vel = pkg.synthetic_velocity(pos, T, seed=1)
     data_h = {"node_type": nt.reshape(1, -1, 1), "mesh_pos": pos[None], "cells": cells[None]}
     node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0, device=dev)
     N, E = pos.shape[0], int(senders.shape[0])
@@ -40,7 +39,7 @@ def main():
         mgn.o_norm["velocity"]((data["velocity"][f + 1] - data["velocity"][f]) / 0.01)
     mgn.e_norm(ef)
     meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}}, "target_features": ["velocity"]}
-    val_mask = to(orc.val_mask(nt, [0, 5], 2))
+    val_mask = to(pkg.val_mask(nt, [0, 5], 2))
     inflow = to(np.repeat((nt == 1)[:, None], 2, axis=1))
     saves = np.arange(0, 51, dtype=np.float32) * np.float32(0.01)
     init = {"velocity": data["velocity"][0]}
