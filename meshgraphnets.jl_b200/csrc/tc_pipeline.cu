@@ -483,6 +483,9 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.f32_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p));
       MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st));
+    } else {  // no edges: the edge MLP of this step has a zero gradient
+      const int64_t lo = m->mlps[2 + 2 * k].w_off[0], hi = m->mlps[3 + 2 * k].w_off[0];
+      MGN_CUDA_TRY(cudaMemsetAsync(dparams + lo, 0, sizeof(float) * (hi - lo), st));
     }
   }
   if (all || stage == MGN_STAGE_ENCODE) {

@@ -114,3 +114,32 @@ def test_ode_step_and_euler_rollout_match_oracle(pkg):
     for i in (1, 2, 5):
         assert rel(sol[i].cpu().numpy() - x0, sol_o[i] - x0) < 1e-3, i
     assert rel(sol[-1].cpu().numpy() - x0, sol_o[-1] - x0) < 1e-3
+
+
+@pytest.mark.parametrize("mode,tol", [(0, 2e-3), (1, 6e-2)])
+def test_50_step_euler_rollout_matches_oracle(pkg, mode, tol):
+    """BASELINE configs[2] shape of the check: state after a 50-step fixed-step rollout through the src/solve.jl RHS
+    mirror (inflow overwrite each step) against the fp64 oracle.  Tolerance on the accumulated state change: 2e-3 in
+    fp32 mode, 6e-2 in the bf16 tensor-core mode (50 RHS evaluations of bf16 arithmetic)."""
+    data_h, data, meta, mgn, (node_type, senders, receivers, ef), o = _setup(pkg, T=52, mode=mode)
+    x0 = data_h["velocity"][0]
+    for n_g, n_o, x in ((mgn.n_norm["velocity"], o["n_norm"]["velocity"], x0),
+                        (mgn.e_norm, o["e_norm"], o["ef"]),
+                        (mgn.o_norm["velocity"], o["o_norm"]["velocity"], (data_h["velocity"][1] - x0) / np.float32(0.01))):
+        n_g(dev(x)); n_o(x)
+        n_g.max_acc = 0.0; n_o.max_acc = np.float32(0)
+    vm_h = orc.val_mask(o["nt"], [0, 5], 2)
+    inflow_h = np.repeat((o["nt"] == 1)[:, None], 2, axis=1)
+    saves = [np.float32(0.01) * i for i in range(51)]
+    sol, ts = pkg.rollout(mgn, {"velocity": dev(x0)}, ["velocity"], meta, ["velocity"], {"velocity": 2}, node_type, ef,
+                          senders, receivers, dev(vm_h), dev(inflow_h), data, 0.0, 0.5, 0.01, saves)
+
+    def inflow_fn(x, t):
+        return np.where(inflow_h, data_h["velocity"][orc.inflow_index(t, saves[1] - saves[0])], x)
+    sol_o = orc.rollout_euler(
+        lambda x, t: orc.ode_step(o["cfg"], o["ps"], x, o["n_norm"], o["e_norm"], o["o_norm"], ["velocity"], ["velocity"],
+                                  [2], {}, o["onehot"], o["ef"], o["s"], o["r"], vm_h, dtype=np.float64),
+        x0, saves, 0.01, inflow_fn)
+    assert len(sol) == 51 and torch.isfinite(sol[-1]).all()
+    for i in (1, 10, 25, 50):
+        assert rel(sol[i].cpu().numpy() - x0, sol_o[i] - x0) < tol, i

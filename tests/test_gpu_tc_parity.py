@@ -186,3 +186,31 @@ def test_chain_100k_nodes_bf16_vs_fp32(pkg):
         res[mode] = (model.forward(graph, ps).cpu().numpy(), float(loss.cpu()), gs.cpu().numpy())
     a, b = res[pkg.COMPUTE_FP32], res[pkg.COMPUTE_BF16]
     assert rel(b[0], a[0]) < TOL_OUT and abs(a[1] - b[1]) < TOL_OUT * abs(a[1]) and rel(b[2], a[2]) < TOL_GRAD
+
+
+def test_bf16_degenerate_graphs(pkg):
+    """Edge cases of the tensor-core path against the fp32 path: no edges at all, and a graph whose tiles contain
+    nodes without incoming edges (aggregation and receiver adjoint must write exact zeros for them)."""
+    rng = np.random.default_rng(4)
+    n = 200
+    nf = dev(rng.normal(size=(n, 9)).astype(np.float32))
+    tgt = dev(rng.normal(size=(n, 2)).astype(np.float32))
+    mask = dev(np.arange(1, n + 1, dtype=np.int32))
+    cfg = orc.ModelConfig(9, 3, 2, 128, 2, 2)
+    ps = dev(orc.init_params(cfg, seed=6))
+    cases = {
+        "no_edges": (np.zeros(0, np.int32), np.zeros(0, np.int32)),
+        "sparse": (rng.integers(1, n + 1, size=60).astype(np.int32), rng.integers(1, 40, size=60).astype(np.int32)),
+    }
+    for name, (s, r) in cases.items():
+        ef = dev(rng.normal(size=(s.shape[0], 3)).astype(np.float32))
+        graph = pkg.FeatureGraph(nf, ef, dev(s), dev(r))
+        res = {}
+        for mode in (pkg.COMPUTE_FP32, pkg.COMPUTE_BF16):
+            model = pkg.Model(9, 3, 2, 2, 128, 2, compute_mode=mode)
+            mgn = pkg.GraphNetwork(model, ps, None, None, None, None)
+            (gs,), loss = pkg.step_(mgn, graph, tgt, mask)
+            res[mode] = (model.forward(graph, ps).cpu().numpy(), float(loss.cpu()), gs.cpu().numpy())
+            assert np.isfinite(res[mode][2]).all(), name
+        a, b = res[pkg.COMPUTE_FP32], res[pkg.COMPUTE_BF16]
+        assert rel(b[0], a[0]) < TOL_OUT and abs(a[1] - b[1]) < TOL_OUT * abs(a[1]) and rel(b[2], a[2]) < TOL_GRAD, name
