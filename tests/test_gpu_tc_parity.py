@@ -214,3 +214,29 @@ def test_bf16_degenerate_graphs(pkg):
             assert np.isfinite(res[mode][2]).all(), name
         a, b = res[pkg.COMPUTE_FP32], res[pkg.COMPUTE_BF16]
         assert rel(b[0], a[0]) < TOL_OUT and abs(a[1] - b[1]) < TOL_OUT * abs(a[1]) and rel(b[2], a[2]) < TOL_GRAD, name
+
+
+@pytest.mark.parametrize("node_in,edge_in,out_dim", [(40, 7, 5), (64, 2, 16), (1, 1, 1)])
+def test_bf16_feature_widths(pkg, node_in, edge_in, out_dim):
+    """Raw feature widths up to the limits of the tensor-core path (<= 64 inputs, <= 16 outputs) against the fp32 path."""
+    rng = np.random.default_rng(8)
+    pos, cells, nt = orc.cylinder_flow_mesh(15, 11)
+    s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
+    N, E = pos.shape[0], s.shape[0]
+    cfg = orc.ModelConfig(node_in, edge_in, out_dim, 128, 2, 2)
+    ps = dev(orc.init_params(cfg, seed=2))
+    graph = pkg.FeatureGraph(dev(rng.normal(size=(N, node_in)).astype(np.float32)),
+                             dev(rng.normal(size=(E, edge_in)).astype(np.float32)), dev(s), dev(r))
+    tgt = dev(rng.normal(size=(N, out_dim)).astype(np.float32))
+    mask = dev(orc.node_mask(nt, [0, 5]))
+    res = {}
+    for mode in (pkg.COMPUTE_FP32, pkg.COMPUTE_BF16):
+        model = pkg.Model(node_in, edge_in, out_dim, 2, 128, 2, compute_mode=mode)
+        mgn = pkg.GraphNetwork(model, ps, None, None, None, None)
+        (gs,), loss = pkg.step_(mgn, graph, tgt, mask)
+        out = model.forward(graph, ps, training=True)
+        dps, dnf = model.backward(graph, ps, torch.ones_like(out) / out.numel(), want_dnf=True)
+        res[mode] = (out.cpu().numpy(), float(loss.cpu()), gs.cpu().numpy(), dnf.cpu().numpy())
+    a, b = res[pkg.COMPUTE_FP32], res[pkg.COMPUTE_BF16]
+    assert rel(b[0], a[0]) < TOL_OUT and abs(a[1] - b[1]) < TOL_OUT * abs(a[1])
+    assert rel(b[2], a[2]) < TOL_GRAD and rel(b[3], a[3]) < 0.2
