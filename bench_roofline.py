@@ -44,6 +44,7 @@ def algorithmic_work(E, N, D, L, mps, node_in, edge_in, out_dim):
     b_node_fwd = 2 * img + f32 + f32 + img + saves + 2 * img       # nf16, agg16, nf32 r/w, nf16', saves | gather src, agg write
     fwd_flops = mps * (f_edge * E + f_node * N)
     fwd_bytes = mps * (b_edge_fwd * E + b_node_fwd * N)
+    fwd_bytes -= (2 * f32 + img) * E             # the edge latent after the last MP step is never read: not updated
     enc_flops = 2 * ((node_in * D + (L - 1) * D2) * N + (edge_in * D + (L - 1) * D2) * E)
     dec_flops = 2 * ((L - 1) * D2 + D * out_dim) * N
     fwd_flops += enc_flops + dec_flops

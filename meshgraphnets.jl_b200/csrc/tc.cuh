@@ -173,11 +173,12 @@ struct InputParams {
 cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st);
 
 // ---- small CUDA-core helpers of the backward pass ---------------------------------------------------
-struct Piece { int64_t src_off; float* dst; int64_t count; };
+struct Piece { const float* src; int64_t stride; int32_t n_parts; float* dst; int64_t count; };
 constexpr int kMaxPieces = 12;
 struct Pieces { Piece p[kMaxPieces]; int n; };
-// dst[i] = sum_k partial[k * stride + src_off + i]   (fixed order: deterministic)
-cudaError_t reduce_pieces(const float* partial, int n_parts, int64_t stride, const Pieces& pieces, cudaStream_t st);
+// For every piece: dst[i] = sum_k src[k * stride + i], k < n_parts   (fixed order: deterministic).  One launch reduces
+// the partials of all kernels of one MLP (chain + input layer, or decoder head + chain + input layer).
+cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st);
 // Decoder head: dZ_{L-2} = (dout W_{L-1}^T) .* (H_{L-2} > 0) as an image, plus per-tile partials of
 // dW_{L-1} [128][od], db_{L-1} [od] and db_{L-2} [128]  (stride 128*od + od + 128 floats per tile).
 cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,

@@ -804,8 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
 // ======================================================================================================
 // Block = 32 outputs x 8 part groups: thread (x, y) sums parts y, y+8, ... of output x (coalesced across x),
 // then the 8 group sums are added in a fixed order -> deterministic, 8x the memory parallelism of a plain loop.
-__global__ void __launch_bounds__(256) reduce_pieces_kernel(const float* __restrict__ partial, int n_parts,
-                                                            int64_t stride, const Pieces pieces, int64_t total) {
+__global__ void __launch_bounds__(256) reduce_pieces_kernel(const Pieces pieces, int64_t total) {
   __shared__ float red[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + x;
@@ -815,7 +814,9 @@ __global__ void __launch_bounds__(256) reduce_pieces_kernel(const float* __restr
     e -= pieces.p[k].count;
     ++k;
   }
-  const float* src = partial + pieces.p[k].src_off + e;
+  const float* src = pieces.p[k].src + e;
+  const int64_t stride = pieces.p[k].stride;
+  const int n_parts = pieces.p[k].n_parts;
   float s = 0.f;
 #pragma unroll 4
   for (int q = y; q < n_parts; q += 8) s += src[(int64_t)q * stride];
@@ -1042,12 +1043,12 @@ cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStrea
   return cudaGetLastError();
 }
 
-cudaError_t reduce_pieces(const float* partial, int n_parts, int64_t stride, const Pieces& pieces, cudaStream_t st) {
+cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st) {
   int64_t total = 0;
   for (int i = 0; i < pieces.n; ++i) total += pieces.p[i].count;
   if (total == 0) return cudaSuccess;
   ProfScope ps(TAG_REDUCE_PARTIALS, st);
-  reduce_pieces_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(partial, n_parts, stride, pieces, total);
+  reduce_pieces_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(pieces, total);
   return cudaGetLastError();
 }
 

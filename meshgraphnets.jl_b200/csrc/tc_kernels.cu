@@ -319,7 +319,8 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         // residual rows are fetched 4 per thread at a time into one half of r0/r1 while the other half is consumed
         float4 r0[8], r1[8];
         const int cc = tid & 15, rg = tid >> 4;
-        const bool resid = p.fin_mode != FIN_LN;
+        const bool resid = p.fin_mode != FIN_LN && p.lat_in != nullptr;
+        const bool write_lat = p.lat_out != nullptr;  // false: only the aggregation is wanted (last MP step's edge latent)
         auto issue_residual = [&](int k, int h) {  // batch k covers rows 32k + rg + 8u
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         //      aggregation is shared-memory bound, so it runs BEFORE the copy-out's burst of global stores fills
         //      the SM's memory pipeline.
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C0: xhat bulk store issued
-        issue_residual(0, 0);
+        if (write_lat) issue_residual(0, 0);
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C1: first residual batch issued
         if (p.fin_mode == FIN_LN_RESID_AGG) {
           const int n0 = rp_s[130], nn = rp_s[131];
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
                             });
         }
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C: aggregation done
-        const bool img_out = p.lat_img_out != nullptr;
+        const bool img_out = write_lat && p.lat_img_out != nullptr;
         if (img_out) {
           // the bf16 shadow of the new latent overwrites the xhat tile in place (same thread, same 16 bytes) and leaves as
           // one bulk store: every reader of xhat (aggregation, the xhat save) must be done first
@@ -435,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         }
         // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced), four batches of
         //      32 rows, the residual rows of batch k+1 in flight while batch k is written
-        {
+        if (write_lat) {
           float sc[8], bi[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {

@@ -108,8 +108,9 @@ struct BwdScratch {
   float *d_nf = nullptr, *d_ef = nullptr, *d_agg = nullptr;  // fp32 gradients of the latents
   __nv_bfloat16* dxs = nullptr;                              // sender adjoint rows as tile images [edge tile][2][16 KB]
   __nv_bfloat16 *dz0 = nullptr, *ztop = nullptr;             // tile images
-  float* partial = nullptr;                                  // per-CTA / per-tile weight-gradient partials
-  size_t partial_floats = 0;
+  // weight-gradient partials of ONE MLP at a time: chain kernel (per CTA), input kernel (per CTA), CUDA-core helper
+  // (per tile: decoder head or encoder input layer) - three regions so that one launch reduces them all
+  float *partial_chain = nullptr, *partial_input = nullptr, *partial_misc = nullptr;
   size_t bytes = 0;
 };
 
@@ -125,11 +126,11 @@ void bwd_layout(const mgn_model* m, const mgn_graph* g, void* base, BwdScratch& 
   b.dz0 = static_cast<__nv_bfloat16*>(bump.raw((size_t)max_tiles * 2 * kTileB));
   b.ztop = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(node_tiles, 1) * 2 * kTileB));
   const int grid = backward_grid((int)max_tiles);
-  size_t pf = (size_t)grid * std::max(chain_partial_floats(kMaxSteps), (size_t)3 * 16384);
-  pf = std::max(pf, (size_t)max_tiles * 64 * 128);                                      // encoder input layer
-  pf = std::max(pf, (size_t)node_tiles * (size_t)(128 * m->cfg.out_dim + m->cfg.out_dim + 128));  // decoder head
-  b.partial_floats = pf;
-  b.partial = bump.f(pf);
+  b.partial_chain = bump.f((size_t)grid * chain_partial_floats(kMaxSteps));
+  b.partial_input = bump.f((size_t)grid * 3 * 16384);
+  const size_t enc_f = (size_t)std::max(m->cfg.node_in, m->cfg.edge_in) * 128;
+  b.partial_misc = bump.f(std::max((size_t)max_tiles * enc_f,
+                                   (size_t)node_tiles * (size_t)(128 * m->cfg.out_dim + m->cfg.out_dim + 128)));
   b.bytes = bump.off;
 }
 
@@ -258,9 +259,11 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.idx0 = g->send_csr;
       p.idx1 = g->recv_csr;
       p.fin_mode = FIN_LN_RESID_AGG;
-      p.lat_in = w.ef32;
-      p.lat_out = w.ef32;
-      p.lat_img_out = w.ef16[nxt];
+      if (k + 1 < mps) {  // the edge latent after the last MP step is never read (the decoder takes the nodes only)
+        p.lat_in = w.ef32;
+        p.lat_out = w.ef32;
+        p.lat_img_out = w.ef16[nxt];
+      }
       p.agg_bf16 = agg;
       MGN_CUDA_TRY(mlp_forward_tc(p, st));
     } else {
@@ -321,7 +324,7 @@ struct BwdCtx {
 // Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
 // LayerNorm (dy = dy_a[r] + dy_b[b_idx[r]]); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
 int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const float* dy_b,
-                  const int32_t* b_idx) {
+                  const int32_t* b_idx, Pieces& pc) {
   const MlpLayout& L = c.m->mlps[mi];
   const MlpImages& im = c.m->images->mlps[mi];
   const MlpSave& sv = c.w->saves[mi];
@@ -353,50 +356,48 @@ int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a,
     p.wt_img[j] = c.w->images + (size_t)im.bwd_off[l] * (kTileB / 2);
   }
   p.dz_out = c.b->dz0;
-  p.partial = c.b->partial;
+  p.partial = c.b->partial_chain;
   int grid = 0;
   MGN_CUDA_TRY(mlp_backward_chain_tc(p, &grid, c.st));
-  Pieces pc{};
-  const int64_t base_db = (int64_t)p.nsteps * 16384;
+  const float* base = c.b->partial_chain;
+  const int64_t stride = (int64_t)chain_partial_floats(p.nsteps), base_db = (int64_t)p.nsteps * 16384;
   for (int j = 0; j < p.nsteps; ++j) {
     const int l = top - j;
-    pc.p[pc.n++] = {(int64_t)j * 16384, c.grads + L.w_off[l], 16384};
-    pc.p[pc.n++] = {base_db + (int64_t)(j + 1) * 128, c.grads + L.b_off[l - 1], 128};
+    pc.p[pc.n++] = {base + (int64_t)j * 16384, stride, grid, c.grads + L.w_off[l], 16384};
+    pc.p[pc.n++] = {base + base_db + (int64_t)(j + 1) * 128, stride, grid, c.grads + L.b_off[l - 1], 128};
   }
   if (L.layer_norm) {
-    pc.p[pc.n++] = {base_db, c.grads + L.b_off[top], 128};
-    pc.p[pc.n++] = {base_db + (int64_t)(p.nsteps + 1) * 128, c.grads + L.ln_scale_off, 128};
-    pc.p[pc.n++] = {base_db + (int64_t)(p.nsteps + 1) * 128 + 128, c.grads + L.ln_bias_off, 128};
+    pc.p[pc.n++] = {base + base_db, stride, grid, c.grads + L.b_off[top], 128};
+    pc.p[pc.n++] = {base + base_db + (int64_t)(p.nsteps + 1) * 128, stride, grid, c.grads + L.ln_scale_off, 128};
+    pc.p[pc.n++] = {base + base_db + (int64_t)(p.nsteps + 1) * 128 + 128, stride, grid, c.grads + L.ln_bias_off, 128};
   }
-  MGN_CUDA_TRY(reduce_pieces(c.b->partial, grid, (int64_t)chain_partial_floats(p.nsteps), pc, c.st));
   return MGN_OK;
 }
 
-int32_t run_input(const BwdCtx& c, size_t mi, InputParams& p) {
+// Input kernel of MLP `mi`, then ONE fixed-order reduction of every partial of this MLP gathered in `pc`.
+int32_t run_input(const BwdCtx& c, size_t mi, InputParams& p, Pieces& pc) {
   const MlpLayout& L = c.m->mlps[mi];
   const MlpImages& im = c.m->images->mlps[mi];
   p.dz0 = (L.layer_norm || L.n_dense > 2) ? c.b->dz0 : c.b->ztop;
   p.wt_img = c.w->images + (size_t)im.bwd_off[0] * (kTileB / 2);
-  p.partial = c.b->partial;
+  p.partial = c.b->partial_input;
   int grid = 0;
   MGN_CUDA_TRY(mlp_backward_input_tc(p, &grid, c.st));
-  Pieces pc{};
-  pc.p[pc.n++] = {0, c.grads + L.w_off[0], (int64_t)p.nblk * 16384};
-  MGN_CUDA_TRY(reduce_pieces(c.b->partial, grid, (int64_t)p.nblk * 16384, pc, c.st));
+  pc.p[pc.n++] = {c.b->partial_input, (int64_t)p.nblk * 16384, grid, c.grads + L.w_off[0], (int64_t)p.nblk * 16384};
+  MGN_CUDA_TRY(reduce_pieces(pc, c.st));
   return MGN_OK;
 }
 
 int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const float* raw, const int32_t* raw_idx,
-                          float* d_raw) {
+                          float* d_raw, Pieces& pc) {
   const MlpLayout& L = c.m->mlps[mi];
   const int n_tiles = edge_rows ? c.g->n_edge_tiles : (int)((c.g->N + kTile - 1) / kTile);
   const int F = L.in[0];
   MGN_CUDA_TRY(encoder_input_bwd(c.b->dz0, raw, raw_idx, F, c.params + L.w_off[0], n_tiles,
                                  edge_rows ? c.g->E : c.g->N, edge_rows ? c.g->tile_row_start : nullptr,
-                                 c.b->partial, d_raw, c.st));
-  Pieces pc{};
-  pc.p[pc.n++] = {0, c.grads + L.w_off[0], (int64_t)F * 128};
-  MGN_CUDA_TRY(reduce_pieces(c.b->partial, n_tiles, (int64_t)F * 128, pc, c.st));
+                                 c.b->partial_misc, d_raw, c.st));
+  pc.p[pc.n++] = {c.b->partial_misc, (int64_t)F * 128, n_tiles, c.grads + L.w_off[0], (int64_t)F * 128};
+  MGN_CUDA_TRY(reduce_pieces(pc, c.st));
   return MGN_OK;
 }
 
@@ -423,13 +424,13 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     const size_t di = m->mlps.size() - 1;
     const MlpLayout& L = m->mlps[di];
     MGN_CUDA_TRY(decoder_head_bwd(dout, od, params + L.w_off[nd - 1], w.saves[di].h[nd - 2], node_tiles, N, b.ztop,
-                                  b.partial, st));
+                                  b.partial_misc, st));
     Pieces pc{};
-    pc.p[pc.n++] = {0, dparams + L.w_off[nd - 1], (int64_t)128 * od};
-    pc.p[pc.n++] = {(int64_t)128 * od, dparams + L.b_off[nd - 1], od};
-    pc.p[pc.n++] = {(int64_t)128 * od + od, dparams + L.b_off[nd - 2], 128};
-    MGN_CUDA_TRY(reduce_pieces(b.partial, node_tiles, (int64_t)128 * od + od + 128, pc, st));
-    MGN_TRY(run_chain(c, di, false, nullptr, nullptr, nullptr));
+    const int64_t hs = (int64_t)128 * od + od + 128;
+    pc.p[pc.n++] = {b.partial_misc, hs, node_tiles, dparams + L.w_off[nd - 1], (int64_t)128 * od};
+    pc.p[pc.n++] = {b.partial_misc + (int64_t)128 * od, hs, node_tiles, dparams + L.b_off[nd - 1], od};
+    pc.p[pc.n++] = {b.partial_misc + (int64_t)128 * od + od, hs, node_tiles, dparams + L.b_off[nd - 2], 128};
+    MGN_TRY(run_chain(c, di, false, nullptr, nullptr, nullptr, pc));
     InputParams p{};
     p.n_tiles = node_tiles;
     p.M = N;
@@ -437,14 +438,15 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     p.x[0] = w.nf16[mps];
     p.sink[0] = SINK_ADD_F32;
     p.f32_dst[0] = b.d_nf;
-    MGN_TRY(run_input(c, di, p));
+    MGN_TRY(run_input(c, di, p, pc));
   }
   for (int k = mps - 1; k >= 0; --k) {
     if (!all && stage != k) continue;
     const bool d_ef_valid = k != mps - 1;  // the decoder does not read the edge latent
     {  // node update: nf[k+1] = nf[k] + LN(MLP_n([nf[k]; agg[k]]))
       const size_t mi = 3 + 2 * k;
-      MGN_TRY(run_chain(c, mi, false, b.d_nf, nullptr, nullptr));
+      Pieces pc{};
+      MGN_TRY(run_chain(c, mi, false, b.d_nf, nullptr, nullptr, pc));
       InputParams p{};
       p.n_tiles = node_tiles;
       p.M = N;
@@ -456,11 +458,12 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.f32_dst[0] = b.d_nf;
       p.sink[1] = SINK_ADD_F32;  // gradient of the aggregated messages
       p.f32_dst[1] = b.d_agg;
-      MGN_TRY(run_input(c, mi, p));
+      MGN_TRY(run_input(c, mi, p, pc));
     }
     if (E > 0) {  // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
       const size_t mi = 2 + 2 * k;
-      MGN_TRY(run_chain(c, mi, true, d_ef_valid ? b.d_ef : nullptr, b.d_agg, g->recv_csr));
+      Pieces pc{};
+      MGN_TRY(run_chain(c, mi, true, d_ef_valid ? b.d_ef : nullptr, b.d_agg, g->recv_csr, pc));
       InputParams p{};
       p.n_tiles = g->n_edge_tiles;
       p.M = E;
@@ -481,7 +484,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.sink[2] = SINK_ADD_F32;     // edge-latent residual
       p.f32_src[2] = d_ef_valid ? b.d_ef : nullptr;
       p.f32_dst[2] = b.d_ef;
-      MGN_TRY(run_input(c, mi, p));
+      MGN_TRY(run_input(c, mi, p, pc));
       MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st));
     } else {  // no edges: the edge MLP of this step has a zero gradient
       const int64_t lo = m->mlps[2 + 2 * k].w_off[0], hi = m->mlps[3 + 2 * k].w_off[0];
@@ -491,14 +494,16 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
   if (all || stage == MGN_STAGE_ENCODE) {
     const MlpLayout& L = m->mlps[1];
     if (mps > 0 && E > 0) {
-      MGN_TRY(run_chain(c, 1, true, b.d_ef, nullptr, nullptr));
-      MGN_TRY(run_encoder_input(c, 1, true, ef, g->perm, nullptr));
+      Pieces pc{};
+      MGN_TRY(run_chain(c, 1, true, b.d_ef, nullptr, nullptr, pc));
+      MGN_TRY(run_encoder_input(c, 1, true, ef, g->perm, nullptr, pc));
     } else {
       const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
     }
-    MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr));
-    MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf));
+    Pieces pc{};
+    MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr, pc));
+    MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf, pc));
   }
   return MGN_OK;
 }
