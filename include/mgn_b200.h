@@ -220,6 +220,49 @@ int32_t mgn_norm_online_apply(const float* d_x, int64_t rows, int32_t features,
 int32_t mgn_affine_apply(const float* d_x, int64_t rows, int32_t features, float scale,
                          float shift, float* d_y, int32_t ld_y, int32_t col_y, void* stream);
 
+/* ------------------------------------------------------------------ NeuralODE callers (src/solve.jl, SolverStrategy of src/strategies.jl) */
+/* The state of the NeuralODE is x [N][S] (S = sum of the target feature dims; src/strategies.jl:171-172).  A solver
+ * strategy evaluates ode_func_train (src/solve.jl:101-115) many times per training step; the pieces of that right-hand
+ * side that are not the model itself, and the pieces of its pullback (what SciMLSensitivity's ZygoteVJP derives,
+ * src/strategies.jl:183-194), are the entry points below.  All of them only enqueue work on `stream`. */
+
+/* One explicit Runge-Kutta combination: y = x + sum_j coef[j] * k[j], j < n_terms <= 8 (stage inputs x + h*sum a_ij k_j,
+ * the update x + h*sum b_i k_i, and - transposed - the adjoint accumulations).  h_k is a HOST array of n_terms DEVICE
+ * pointers, h_coef a HOST array; d_x may be NULL (treated as zero); d_y may alias d_x or any k[j].  Every product and
+ * sum is rounded separately in ascending j (what the broadcast `x .+ c1 .* k1 .+ ...` does). */
+int32_t mgn_ode_lincomb(const float* d_x, const float* const* h_k, const float* h_coef, int32_t n_terms, int64_t n,
+                        float* d_y, void* stream);
+/* Inflow overwrite `bx[inflow_mask] = data[...][inflow_mask]`  <- src/solve.jl:104-107 (train), :151 (eval):
+ * y[i] = mask[i] ? src[i] : x[i].  With d_src == NULL it is the transposed Jacobian: y[i] = mask[i] ? 0 : x[i]. */
+int32_t mgn_masked_overwrite(const float* d_x, const float* d_src, const uint8_t* d_mask, int64_t n, float* d_y,
+                             void* stream);
+/* `copy(buf) .* val_mask`  <- src/solve.jl:218 (and its pullback): y = a .* b. */
+int32_t mgn_vec_mul(const float* d_a, const float* d_b, int64_t n, float* d_y, void* stream);
+
+/* Strided normaliser maps without accumulation: x is read from columns [col_x, col_x + features) of a matrix with
+ * leading dimension ld_x, y written likewise.  FORWARD / INVERSE are mgn_norm_online_apply's two directions; the _VJP
+ * modes are their transposed Jacobians (dy / std and dy * std), used by the pullback of build_graph (src/graph.jl:80-86)
+ * and of inverse_data (src/solve.jl:205-210). */
+enum { MGN_NORM_FORWARD = 0, MGN_NORM_INVERSE = 1, MGN_NORM_FORWARD_VJP = 2, MGN_NORM_INVERSE_VJP = 3 };
+int32_t mgn_norm_online_apply_ld(const float* d_x, int32_t ld_x, int32_t col_x, int64_t rows, int32_t features,
+                                 const float* d_state, float std_eps, int32_t mode, float* d_y, int32_t ld_y,
+                                 int32_t col_y, void* stream);
+int32_t mgn_affine_apply_ld(const float* d_x, int32_t ld_x, int32_t col_x, int64_t rows, int32_t features,
+                            float scale, float shift, float* d_y, int32_t ld_y, int32_t col_y, void* stream);
+
+/* train_loss(::SolverTraining)  <- src/strategies.jl:253-286, and the per-interval error term of
+ * train_loss(::MultipleShooting)  <- src/strategies.jl:367-378:  with e = (gt - pred).^2 .* val_mask over n_saves saved
+ * states of mask_elems = N*S values each,  d_loss[0] = (accumulate ? d_loss[0] : 0) + weight * sum(e)  (weight =
+ * 1 / (n_saves * mask_elems) gives `mean`), and d_dpred = d loss / d pred.  Fixed summation order (deterministic).
+ * The first call on a device allocates 1 KB of scratch (do it once outside CUDA-graph capture). */
+int32_t mgn_shooting_mse(const float* d_pred, const float* d_gt, const float* d_val_mask, int64_t n_saves,
+                         int64_t mask_elems, float weight, int32_t accumulate, float* d_loss, float* d_dpred,
+                         void* stream);
+/* Continuity term `continuity_term * sum(abs, pred_prev[:, :, end] - gt[:, :, first(rg)])`  <- src/strategies.jl:380-383:
+ * d_loss[0] += weight * sum|a - b| and d_da += weight * sign(a - b)  (d_da is ACCUMULATED into). */
+int32_t mgn_shooting_continuity(const float* d_a, const float* d_b, int64_t n, float weight, float* d_loss,
+                                float* d_da, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,8 @@ csrc/            CUDA kernels + the C ABI (libmgn_b200.so, include/mgn_b200.h)
 core.py          host mirror of the GraphNetCore.jl names MeshGraphNets.jl calls
 graph.py         mirror of src/graph.jl      (create_base_graph, build_graph)
 solve.py         mirror of src/solve.jl      (ode_step, ode_func_eval, rollout)
-strategies.py    mirror of src/strategies.jl (DerivativeTraining step)
+strategies.py    mirror of src/strategies.jl (DerivativeTraining, SolverTraining, MultipleShooting steps)
+shooting.py      lock-step shooting intervals: fixed-step Runge-Kutta solve + exact reverse sweep over the C ABI
 partition.py     graph partitioning + halo exchange for meshes larger than one GPU
 workloads.py     synthetic BASELINE workloads + the driver's mask helpers (src/MeshGraphNets.jl:352-358)
 parallel.py      data-parallel plumbing (window sharding, gradient / normaliser all-reduce)
@@ -20,9 +21,13 @@ from .parallel import allreduce_mean_, allreduce_normaliser_, shard_windows  # n
 from .partition import (DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
                         build_partition_rank,
                         masked_mse_partial, partition_bounds, run_partitioned_step)
+from ._lib import NORM_FORWARD, NORM_FORWARD_VJP, NORM_INVERSE, NORM_INVERSE_VJP  # noqa: F401
 from ._lib import (HALO_GRAD, HALO_LATENT, ROWS_ADD, ROWS_PACK, ROWS_PACK_ZERO, ROWS_UNPACK, STAGE_DECODE,  # noqa: F401
                    STAGE_ENCODE)
 from .solve import ode_func_eval, ode_step, rollout  # noqa: F401
 from .workloads import (chain_edges, cylinder_flow_mesh, node_mask, synthetic_velocity, tet_grid_edges,  # noqa: F401
                         val_mask)
-from .strategies import DerivativeTraining, get_delta, init_train_step, train_step  # noqa: F401
+from .strategies import (DerivativeTraining, MultipleShooting, SolverTraining, get_delta, init_train_step,  # noqa: F401
+                         train_step)
+from .shooting import (DeviceAlgebra, DeviceRhs, RK_TABLEAUS, ShootingEngine, multiple_shooting_step,  # noqa: F401
+                       shard_intervals, shooting_ranges, solver_training_step, time_steps)

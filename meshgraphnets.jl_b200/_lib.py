@@ -15,6 +15,7 @@ COMPUTE_BF16 = 1
 STAGE_ENCODE, STAGE_DECODE = -1, -2
 HALO_LATENT, HALO_GRAD = 0, 1
 ROWS_PACK, ROWS_UNPACK, ROWS_ADD, ROWS_PACK_ZERO = 0, 1, 2, 3
+NORM_FORWARD, NORM_INVERSE, NORM_FORWARD_VJP, NORM_INVERSE_VJP = 0, 1, 2, 3
 
 
 class MgnError(RuntimeError):
@@ -72,6 +73,13 @@ SIGNATURES = {
     "mgn_norm_online_update": [_p, _i64, _i32, _p, _f32, _p],
     "mgn_norm_online_apply": [_p, _i64, _i32, _p, _f32, _i32, _p, _i32, _i32, _p],
     "mgn_affine_apply": [_p, _i64, _i32, _f32, _f32, _p, _i32, _i32, _p],
+    "mgn_ode_lincomb": [_p, _p, _p, _i32, _i64, _p, _p],
+    "mgn_masked_overwrite": [_p, _p, _p, _i64, _p, _p],
+    "mgn_vec_mul": [_p, _p, _i64, _p, _p],
+    "mgn_norm_online_apply_ld": [_p, _i32, _i32, _i64, _i32, _p, _f32, _i32, _p, _i32, _i32, _p],
+    "mgn_affine_apply_ld": [_p, _i32, _i32, _i64, _i32, _f32, _f32, _p, _i32, _i32, _p],
+    "mgn_shooting_mse": [_p, _p, _p, _i64, _i64, _f32, _i32, _p, _p, _p],
+    "mgn_shooting_continuity": [_p, _p, _i64, _f32, _p, _p, _p],
 }
 
 _lib = None

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libmgn_b200.so")
-SOURCES = ["abi.cu", "csr.cu", "simt_kernels.cu", "pipeline.cu", "tc_probe.cu", "tc_kernels.cu", "tc_bwd_kernels.cu", "tc_pipeline.cu"]
+SOURCES = ["abi.cu", "csr.cu", "simt_kernels.cu", "solver_kernels.cu", "pipeline.cu", "tc_probe.cu", "tc_kernels.cu", "tc_bwd_kernels.cu", "tc_pipeline.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -204,6 +204,11 @@ class NormaliserOfflineMinMax:
         a, c = self._affine()
         return _affine(y, 1.0 / a, -c / a, out, col)
 
+    def apply_ld(self, x, col_x, width, mode, out, col_out):
+        """Strided map / transposed Jacobian (``_lib.NORM_*`` modes) used by the solver strategies."""
+        a, c = self._affine()
+        return _affine_ld(x, col_x, width, *_affine_mode(a, c, mode), out, col_out)
+
 
 class NormaliserOfflineMeanStd:
     """GraphNetCore.NormaliserOfflineMeanStd(mean, std)."""
@@ -217,6 +222,10 @@ class NormaliserOfflineMeanStd:
     def inverse(self, y, out=None, col=0):
         return _affine(y, float(self.std), float(self.mean), out, col)
 
+    def apply_ld(self, x, col_x, width, mode, out, col_out):
+        a, c = float(1.0 / self.std), float(-self.mean / self.std)
+        return _affine_ld(x, col_x, width, *_affine_mode(a, c, mode), out, col_out)
+
 
 def _affine(x, a, c, out, col):
     x = _dev_f32(x, "x")
@@ -224,6 +233,19 @@ def _affine(x, a, c, out, col):
     if out is None:
         out, col = torch.empty_like(x), 0
     call("mgn_affine_apply", _ptr(x), rows, F, a, c, _ptr(out), out.shape[1], col, _stream())
+    return out
+
+
+def _affine_mode(a, c, mode):
+    """(scale, shift) of y = a x + c in the four ``_lib.NORM_*`` modes."""
+    return {_lib.NORM_FORWARD: (a, c), _lib.NORM_INVERSE: (1.0 / a, -c / a),
+            _lib.NORM_FORWARD_VJP: (a, 0.0), _lib.NORM_INVERSE_VJP: (1.0 / a, 0.0)}[mode]
+
+
+def _affine_ld(x, col_x, width, scale, shift, out, col_out):
+    x, out = _dev_f32(x, "x"), _dev_f32(out, "out")
+    call("mgn_affine_apply_ld", _ptr(x), x.shape[1], int(col_x), x.shape[0], int(width), float(scale), float(shift),
+         _ptr(out), out.shape[1], int(col_out), _stream())
     return out
 
 
@@ -259,6 +281,19 @@ class NormaliserOnline:
         call("mgn_norm_online_apply", _ptr(y), rows, F, _ptr(self.state), self.std_epsilon, 1, _ptr(out),
              out.shape[1], col, _stream())
         return out
+
+
+def _online_apply_ld(self, x, col_x, width, mode, out, col_out):
+    """Strided map / transposed Jacobian from the CURRENT statistics; never accumulates."""
+    x, out = _dev_f32(x, "x"), _dev_f32(out, "out")
+    if width != self.dim:
+        raise ValueError(f"NormaliserOnline({self.dim}) applied to {width} features")
+    call("mgn_norm_online_apply_ld", _ptr(x), x.shape[1], int(col_x), x.shape[0], int(width), _ptr(self.state),
+         self.std_epsilon, int(mode), _ptr(out), out.shape[1], int(col_out), _stream())
+    return out
+
+
+NormaliserOnline.apply_ld = _online_apply_ld
 
 
 def inverse_data(norm, y):
@@ -302,19 +337,27 @@ class Model:
         call("mgn_model_param_layout", self._h, arr, n.value, C.byref(n))
         return [(e.name.decode(), e.offset, e.rows, e.cols) for e in arr]
 
-    def workspace(self, gi: GraphIndex, training: bool):
-        key = (id(gi), bool(training))
+    def workspace(self, gi: GraphIndex, training: bool, slot=0):
+        """``slot`` > 0 gives further workspaces for the same graph: the stages of one Runge-Kutta step keep their
+        activations side by side until the reverse sweep has consumed them (solver strategies)."""
+        key = (id(gi), bool(training), int(slot))
         ws = self._ws.get(key)
         if ws is None:
             nbytes = C.c_size_t(0)
             call("mgn_workspace_bytes", self._h, gi._h, int(training), C.byref(nbytes))
-            if len(self._ws) > 8:
-                self._ws.clear()
+            if len(self._ws) > 16:   # evict other graphs only: the slots of this one may hold a step in flight
+                for k in [k for k in self._ws if k[0] != id(gi)]:
+                    del self._ws[k]
             ws = (torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device="cuda"), gi)
             self._ws[key] = ws
         return ws[0]
 
-    def forward(self, graph: FeatureGraph, ps, training=False):
+    def workspace_bytes(self, gi: GraphIndex, training: bool):
+        nbytes = C.c_size_t(0)
+        call("mgn_workspace_bytes", self._h, gi._h, int(training), C.byref(nbytes))
+        return nbytes.value
+
+    def forward(self, graph: FeatureGraph, ps, training=False, slot=0):
         gi = graph.index
         nf = _dev_f32(graph.node_features, "node_features")
         ef = _dev_f32(graph.edge_features, "edge_features")
@@ -323,16 +366,16 @@ class Model:
             raise ValueError(f"ps has {ps.numel()} elements, model needs {self.n_params}")
         if nf.shape[1] != self.cfg.node_in or ef.shape[1] != self.cfg.edge_in:
             raise ValueError("feature widths do not match the model")
-        ws = self.workspace(gi, training)
+        ws = self.workspace(gi, training, slot)
         out = torch.empty((nf.shape[0], self.cfg.out_dim), dtype=torch.float32, device=nf.device)
         call("mgn_forward", self._h, gi._h, _ptr(ps), _ptr(nf), _ptr(ef), _ptr(out), _ptr(ws), ws.numel(),
              int(training), _stream())
         return out
 
-    def backward(self, graph: FeatureGraph, ps, dout, want_dnf=False):
+    def backward(self, graph: FeatureGraph, ps, dout, want_dnf=False, slot=0):
         """Pullback of the matching ``forward(..., training=True)``: (d_ps, d_nf or None)."""
         gi = graph.index
-        ws = self.workspace(gi, True)
+        ws = self.workspace(gi, True, slot)
         nf = _dev_f32(graph.node_features, "node_features")
         ef = _dev_f32(graph.edge_features, "edge_features")
         dout = _dev_f32(dout, "dout")

@@ -24,7 +24,7 @@ int32_t fail(int32_t code, const std::string& msg) {
 static const char* kTagNames[TAG_COUNT] = {
     "simt_gemm_fwd", "simt_gemm_dx", "simt_dw", "reduce_partials", "segment_sum", "ln_bwd", "ln_reduce",
     "node_grad_gather", "add_cols", "loss", "adam", "normaliser", "tc_pack", "tc_mlp_fwd", "tc_mlp_bwd",
-    "tc_dw", "tc_misc"};
+    "tc_dw", "tc_misc", "solver"};
 const char* tag_name(int tag) { return tag >= 0 && tag < TAG_COUNT ? kTagNames[tag] : "?"; }
 
 struct Profiler {
@@ -498,6 +498,71 @@ int32_t mgn_affine_apply(const float* d_x, int64_t rows, int32_t features, float
   MGN_REQUIRE(ld_y >= features + col_y && col_y >= 0, "affine_apply: bad ld_y / col_y");
   MGN_CUDA_TRY(affine_apply(d_x, rows, features, scale, shift, d_y, ld_y, col_y,
                             static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// NeuralODE callers (src/solve.jl, SolverStrategy of src/strategies.jl)
+// ------------------------------------------------------------------------------------------
+int32_t mgn_ode_lincomb(const float* d_x, const float* const* h_k, const float* h_coef, int32_t n_terms, int64_t n,
+                        float* d_y, void* stream) {
+  MGN_REQUIRE(d_y && n >= 0, "ode_lincomb: bad argument");
+  MGN_REQUIRE(n_terms >= 0 && n_terms <= kOdeMaxTerms, "ode_lincomb: n_terms must be in [0, 8]");
+  MGN_REQUIRE(n_terms == 0 || (h_k && h_coef), "ode_lincomb: null term list");
+  for (int j = 0; j < n_terms; ++j) MGN_REQUIRE(h_k[j], "ode_lincomb: null term");
+  MGN_CUDA_TRY(ode_lincomb(d_x, h_k, h_coef, n_terms, n, d_y, static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_masked_overwrite(const float* d_x, const float* d_src, const uint8_t* d_mask, int64_t n, float* d_y,
+                             void* stream) {
+  MGN_REQUIRE(d_x && d_mask && d_y && n >= 0, "masked_overwrite: bad argument");
+  MGN_CUDA_TRY(masked_overwrite(d_x, d_src, d_mask, n, d_y, static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_vec_mul(const float* d_a, const float* d_b, int64_t n, float* d_y, void* stream) {
+  MGN_REQUIRE(d_a && d_b && d_y && n >= 0, "vec_mul: bad argument");
+  MGN_CUDA_TRY(vec_mul(d_a, d_b, n, d_y, static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_norm_online_apply_ld(const float* d_x, int32_t ld_x, int32_t col_x, int64_t rows, int32_t features,
+                                 const float* d_state, float std_eps, int32_t mode, float* d_y, int32_t ld_y,
+                                 int32_t col_y, void* stream) {
+  MGN_REQUIRE(d_x && d_state && d_y && rows >= 0 && features > 0, "norm_online_apply_ld: bad argument");
+  MGN_REQUIRE(mode >= MGN_NORM_FORWARD && mode <= MGN_NORM_INVERSE_VJP, "norm_online_apply_ld: unknown mode");
+  MGN_REQUIRE(col_x >= 0 && ld_x >= features + col_x, "norm_online_apply_ld: bad ld_x / col_x");
+  MGN_REQUIRE(col_y >= 0 && ld_y >= features + col_y, "norm_online_apply_ld: bad ld_y / col_y");
+  MGN_CUDA_TRY(norm_online_apply_ld(d_x, ld_x, col_x, rows, features, d_state, std_eps, mode, d_y, ld_y, col_y,
+                                    static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_affine_apply_ld(const float* d_x, int32_t ld_x, int32_t col_x, int64_t rows, int32_t features,
+                            float scale, float shift, float* d_y, int32_t ld_y, int32_t col_y, void* stream) {
+  MGN_REQUIRE(d_x && d_y && rows >= 0 && features > 0, "affine_apply_ld: bad argument");
+  MGN_REQUIRE(col_x >= 0 && ld_x >= features + col_x, "affine_apply_ld: bad ld_x / col_x");
+  MGN_REQUIRE(col_y >= 0 && ld_y >= features + col_y, "affine_apply_ld: bad ld_y / col_y");
+  MGN_CUDA_TRY(affine_apply_ld(d_x, ld_x, col_x, rows, features, scale, shift, d_y, ld_y, col_y,
+                               static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_shooting_mse(const float* d_pred, const float* d_gt, const float* d_val_mask, int64_t n_saves,
+                         int64_t mask_elems, float weight, int32_t accumulate, float* d_loss, float* d_dpred,
+                         void* stream) {
+  MGN_REQUIRE(d_pred && d_gt && d_val_mask && d_loss && d_dpred, "shooting_mse: null argument");
+  MGN_REQUIRE(n_saves > 0 && mask_elems > 0, "shooting_mse: bad sizes");
+  MGN_CUDA_TRY(shooting_mse(d_pred, d_gt, d_val_mask, mask_elems, n_saves * mask_elems, weight, accumulate, d_loss,
+                            d_dpred, static_cast<cudaStream_t>(stream)));
+  return MGN_OK;
+}
+
+int32_t mgn_shooting_continuity(const float* d_a, const float* d_b, int64_t n, float weight, float* d_loss,
+                                float* d_da, void* stream) {
+  MGN_REQUIRE(d_a && d_b && d_loss && d_da && n > 0, "shooting_continuity: bad argument");
+  MGN_CUDA_TRY(shooting_continuity(d_a, d_b, n, weight, d_loss, d_da, static_cast<cudaStream_t>(stream)));
   return MGN_OK;
 }
 

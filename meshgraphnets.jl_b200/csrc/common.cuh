@@ -33,12 +33,13 @@ int32_t fail(int32_t code, const std::string& msg);
   } while (0)
 
 constexpr int kMaxDense = 8;
+constexpr int kOdeMaxTerms = 8;  // terms of one explicit Runge-Kutta combination (mgn_ode_lincomb)
 
 // ---- launch counter / per-kernel-family device timer (mgn_profile_begin / mgn_profile_end) ------
 enum KernelTag : int {
   TAG_SIMT_GEMM_FWD = 0, TAG_SIMT_GEMM_DX, TAG_SIMT_DW, TAG_REDUCE_PARTIALS, TAG_SEGMENT_SUM,
   TAG_LN_BWD, TAG_LN_REDUCE, TAG_NODE_GRAD_GATHER, TAG_ADD_COLS, TAG_LOSS, TAG_ADAM, TAG_NORM,
-  TAG_TC_PACK, TAG_TC_MLP_FWD, TAG_TC_MLP_BWD, TAG_TC_DW, TAG_TC_MISC, TAG_COUNT
+  TAG_TC_PACK, TAG_TC_MLP_FWD, TAG_TC_MLP_BWD, TAG_TC_DW, TAG_TC_MISC, TAG_SOLVER, TAG_COUNT
 };
 const char* tag_name(int tag);
 struct ProfScope {  // records a CUDA event pair around one launch when its family is being timed
@@ -164,6 +165,21 @@ cudaError_t norm_online_apply(const float* x, int64_t rows, int F, const float* 
                               cudaStream_t st);
 cudaError_t affine_apply(const float* x, int64_t rows, int F, float scale, float shift, float* y,
                          int ld_y, int col_y, cudaStream_t st);
+
+// ---- NeuralODE callers: solver_kernels.cu -----------------------------------------------------
+cudaError_t ode_lincomb(const float* x, const float* const* k, const float* coef, int n_terms, int64_t n, float* y,
+                        cudaStream_t st);
+cudaError_t masked_overwrite(const float* x, const float* src, const uint8_t* mask, int64_t n, float* y,
+                             cudaStream_t st);
+cudaError_t vec_mul(const float* a, const float* b, int64_t n, float* y, cudaStream_t st);
+cudaError_t norm_online_apply_ld(const float* x, int ld_x, int col_x, int64_t rows, int F, const float* state,
+                                 float std_eps, int mode, float* y, int ld_y, int col_y, cudaStream_t st);
+cudaError_t affine_apply_ld(const float* x, int ld_x, int col_x, int64_t rows, int F, float scale, float shift,
+                            float* y, int ld_y, int col_y, cudaStream_t st);
+cudaError_t shooting_mse(const float* pred, const float* gt, const float* vm, int64_t period, int64_t n, float w,
+                         int accumulate, float* loss, float* dpred, cudaStream_t st);
+cudaError_t shooting_continuity(const float* a, const float* b, int64_t n, float w, float* loss, float* da,
+                                cudaStream_t st);
 
 // ---- CSR build: csr.cu -----------------------------------------------------------------------
 int32_t build_graph_index(mgn_graph* g, const int32_t* d_senders, const int32_t* d_receivers,

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Solver-strategy training step on one B200 (src/strategies.jl MultipleShooting / SolverTraining through the host
+mirror): CylinderFlow-shaped mesh, 15 MP steps, tsteps = 0:0.01:0.49 (50 observations), interval_size 6 -> 10 shooting
+intervals.  Times one train_step (lock-step solve + reverse sweep) with CUDA events and, for comparison, the same step
+with the intervals solved one after the other (the reference's order, strategies.jl:349-362) through the same
+kernels.  Prints one JSON line per configuration."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT]
+import mgn_pkg  # noqa: E402
+
+pkg = mgn_pkg.pkg
+
+
+def timed(fn, reps):
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def main():
+    mode = pkg.COMPUTE_BF16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else pkg.COMPUTE_FP32
+    dev = torch.device("cuda", 0)
+    pos, cells, nt = pkg.cylinder_flow_mesh(65, 29)
+    T = 50
+    vel = pkg.synthetic_velocity(pos, T + 1, seed=1)
+    data_h = {"node_type": nt.reshape(1, -1, 1), "mesh_pos": pos[None], "cells": cells[None]}
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0, device=dev)
+    N, E = pos.shape[0], int(senders.shape[0])
+    model, ps, st = pkg.build_model(9, 2, 2, 15, 128, 2, device=dev, compute_mode=mode)
+    mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOnline(3, dev),
+                           {"velocity": pkg.NormaliserOnline(2, dev), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
+                           {"velocity": pkg.NormaliserOnline(2, dev)})
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    data = {"velocity": to(vel[:T]), "target|velocity": to(vel[1:T + 1]), "node_type": to(nt.reshape(1, -1, 1).astype(np.int32))}
+    for f in range(3):
+        mgn.n_norm["velocity"](data["velocity"][f])
+        mgn.o_norm["velocity"]((data["velocity"][f + 1] - data["velocity"][f]) / 0.01)
+    mgn.e_norm(ef)
+    meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}}, "target_features": ["velocity"]}
+    vm = to(pkg.val_mask(nt, [0, 5], 2))
+    t = (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders, receivers, 1, None, vm)
+    n_int = len(pkg.shooting_ranges(50, 6))
+    for solver in ("euler", "tsit5"):
+        stages = len(pkg.RK_TABLEAUS[solver][2])
+        strat = pkg.MultipleShooting(0.0, 0.01, 0.49, solver, interval_size=6, continuity_term=100)
+        tt = pkg.init_train_step(strat, t, None)
+        ms, ((gs,), loss) = timed(lambda: pkg.train_step(strat, tt), 3)
+
+        def sequential():
+            g, l = None, 0.0
+            for i in range(n_int):
+                s = pkg.MultipleShooting(0.0, 0.01, 0.49, solver, interval_size=6, continuity_term=100, rank=i, world=n_int)
+                (gi,), li = pkg.train_step(s, tt)
+                g = gi if g is None else g + gi
+                l = l + li
+            return (g,), l
+        ms_seq, ((gs_seq,), loss_seq) = timed(sequential, 1)
+        # RHS evaluations of one step: forward sweep (5 steps x stages) + reverse sweep (5 x stages fwd+bwd), K intervals each
+        rhs_fwd, rhs_bwd = 2 * 5 * stages, 5 * stages
+        print(json.dumps({
+            "workload": "cylinder_flow_multiple_shooting_step", "nodes": N, "edges": E, "mps": 15,
+            "mode": "bf16" if mode == pkg.COMPUTE_BF16 else "fp32", "solver": solver, "intervals": n_int,
+            "interval_size": 6, "ms_per_train_step_lockstep": ms, "ms_per_train_step_sequential": ms_seq,
+            "speedup_lockstep": ms_seq / ms, "rhs_forward_evals": rhs_fwd, "rhs_backward_evals": rhs_bwd,
+            # in units of one forward+backward pass (a forward-only evaluation counts 1/3, the FLOP convention of bench.py)
+            "mp_step_edges_per_sec_train_equiv": (rhs_bwd + (rhs_fwd - rhs_bwd) / 3) * n_int * E * 15 / (ms * 1e-3),
+            "loss": float(loss.cpu()), "loss_sequential": float(loss_seq.cpu()),
+            "grad_rel_diff_vs_sequential": float(((gs - gs_seq).norm() / gs_seq.norm()).cpu())}), flush=True)
+    strat = pkg.SolverTraining(0.0, 0.01, 0.49, "euler")
+    ms, ((gs,), loss) = timed(lambda: pkg.train_step(strat, pkg.init_train_step(strat, t, None)), 2)
+    print(json.dumps({"workload": "cylinder_flow_solver_training_step", "solver": "euler", "saves": 50,
+                      "mode": "bf16" if mode == pkg.COMPUTE_BF16 else "fp32", "ms_per_train_step": ms,
+                      "loss": float(loss.cpu()), "grad_finite": bool(torch.isfinite(gs).all())}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
