@@ -78,6 +78,26 @@ def inflow_index(t, strategy_dt, n_data):
 # Device implementations of the two interfaces
 # ------------------------------------------------------------------------------------------------------------------
 
+_mesh_cache: dict = {}
+
+
+def _block_diagonal(senders, receivers, n_nodes, K):
+    """Index vectors of K disjoint copies of the mesh (node ids of copy k shifted by k*N, index base kept).  Cached per
+    (senders, receivers, K): every training step of a trajectory then reuses the same tensors, hence the same device
+    CSR (core.graph_index_for keys on their addresses) and the same workspaces."""
+    key = (senders.data_ptr(), receivers.data_ptr(), int(n_nodes), int(senders.shape[0]), int(K))
+    hit = _mesh_cache.get(key)
+    if hit is None:
+        if len(_mesh_cache) >= 4:
+            _mesh_cache.pop(next(iter(_mesh_cache)))
+        shift = (torch.arange(K, device=senders.device, dtype=torch.int32) * int(n_nodes)).repeat_interleave(
+            int(senders.shape[0]))
+        # the entry keeps the source tensors alive so that their addresses cannot be reused by another mesh
+        hit = ((senders.repeat(K) + shift).contiguous(), (receivers.repeat(K) + shift).contiguous(), senders, receivers)
+        _mesh_cache[key] = hit
+    return hit[0], hit[1]
+
+
 
 class DeviceAlgebra:
     """Elementwise and loss kernels of libmgn_b200 (include/mgn_b200.h, "NeuralODE callers")."""
@@ -129,11 +149,8 @@ class DeviceRhs:
             self.cols[f] = (off, int(target_dict[f]))
             off += int(target_dict[f])
         self.S = off
-        K, N, E = self.K, self.N, int(senders.shape[0])
-        dev = node_type.device
-        shift = (torch.arange(K, device=dev, dtype=torch.int32) * N).repeat_interleave(E)
-        self.senders = (senders.repeat(K) + shift).contiguous()
-        self.receivers = (receivers.repeat(K) + shift).contiguous()
+        K, N = self.K, self.N
+        self.senders, self.receivers = _block_diagonal(senders, receivers, N, K)
         self.node_type = node_type.repeat(K, 1).contiguous()
         self.inputs = {f: _dev_f32(inputs[f], f).repeat(K, 1).contiguous() for f in self.fields if f not in self.cols}
         self.widths = [self.cols[f][1] if f in self.cols else self.inputs[f].shape[1] for f in self.fields]
