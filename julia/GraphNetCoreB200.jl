@@ -109,4 +109,48 @@ function step!(mgn, g, target::CuMatrix{Float32}, mask::CuVector{Int32}, _loss)
     (dps,), loss                                  # gs is iterated at src/MeshGraphNets.jl:375-377
 end
 
+# ---- NeuralODE callers (include/mgn_b200.h, "NeuralODE callers") -----------------------------------------------
+# The solver strategies (src/strategies.jl:229-386) need nothing beyond the rrule above: OrdinaryDiffEq drives
+# ode_func_train and SciMLSensitivity's ZygoteVJP pulls it back through `rrule(::B200Model, ...)`.  The entry points
+# below let the REST of the right-hand side stay on the device without allocating broadcasts: the inflow overwrite
+# (src/solve.jl:104-107), `.* val_mask` (:218), Runge-Kutta stage combinations, and the shooting losses
+# (src/strategies.jl:263-286, :367-383).  meshgraphnets.jl_b200/shooting.py is the executable specification of how
+# they compose into a lock-step MultipleShooting step (all intervals as one block-diagonal graph).
+stream() = CUDA.stream().handle
+
+# y = x + sum_j coef[j] * k[j]   (n_terms <= 8)
+function ode_lincomb!(y::CuArray{Float32}, x::CuArray{Float32}, ks::Vector{<:CuArray{Float32}}, coef::Vector{Float32})
+    ptrs = [reinterpret(Ptr{Cvoid}, pointer(k)) for k in ks]
+    GC.@preserve ks check(ccall((:mgn_ode_lincomb, LIB), Int32,
+        (CuPtr{Float32}, Ptr{Ptr{Cvoid}}, Ptr{Float32}, Int32, Int64, CuPtr{Float32}, Ptr{Cvoid}),
+        x, ptrs, coef, length(ks), length(y), y, stream()))
+    y
+end
+
+# bx[inflow_mask] = data[inflow_mask]   (mask::CuArray{UInt8}; src == nothing gives the transposed Jacobian)
+function masked_overwrite!(y, x, src, mask::CuArray{UInt8})
+    check(ccall((:mgn_masked_overwrite, LIB), Int32,
+        (CuPtr{Float32}, CuPtr{Float32}, CuPtr{UInt8}, Int64, CuPtr{Float32}, Ptr{Cvoid}),
+        x, src === nothing ? CuPtr{Float32}(0) : src, mask, length(y), y, stream()))
+    y
+end
+
+vec_mul!(y, a, b) = (check(ccall((:mgn_vec_mul, LIB), Int32,
+    (CuPtr{Float32}, CuPtr{Float32}, Int64, CuPtr{Float32}, Ptr{Cvoid}), a, b, length(y), y, stream())); y)
+
+# mean((gt .- pred).^2 .* val_mask) over n_saves saved states and its gradient w.r.t. pred
+function shooting_mse!(loss::CuVector{Float32}, dpred, pred, gt, val_mask; accumulate = false)
+    n_saves = size(pred, 3)
+    check(ccall((:mgn_shooting_mse, LIB), Int32,
+        (CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Int64, Float32, Int32, CuPtr{Float32},
+         CuPtr{Float32}, Ptr{Cvoid}),
+        pred, gt, val_mask, n_saves, length(val_mask), 1.0f0 / length(pred), accumulate, loss, dpred, stream()))
+    loss
+end
+
+# loss += w * sum(abs, a .- b); da .+= w .* sign.(a .- b)
+shooting_continuity!(loss, da, a, b, w) = (check(ccall((:mgn_shooting_continuity, LIB), Int32,
+    (CuPtr{Float32}, CuPtr{Float32}, Int64, Float32, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
+    a, b, length(a), Float32(w), loss, da, stream())); loss)
+
 end # module

@@ -17,14 +17,14 @@ from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, Normalis
                    shift_one_based, step_,
                    triangles_to_edges)
 from .graph import build_graph, create_base_graph  # noqa: F401
-from .parallel import allreduce_mean_, allreduce_normaliser_, shard_windows  # noqa: F401
+from .parallel import allreduce_mean_, allreduce_normaliser_, allreduce_sum_, shard_windows  # noqa: F401
 from .partition import (DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
                         build_partition_rank,
                         masked_mse_partial, partition_bounds, run_partitioned_step)
 from ._lib import NORM_FORWARD, NORM_FORWARD_VJP, NORM_INVERSE, NORM_INVERSE_VJP  # noqa: F401
 from ._lib import (HALO_GRAD, HALO_LATENT, ROWS_ADD, ROWS_PACK, ROWS_PACK_ZERO, ROWS_UNPACK, STAGE_DECODE,  # noqa: F401
                    STAGE_ENCODE)
-from .solve import ode_func_eval, ode_step, rollout  # noqa: F401
+from .solve import CapturedRollout, ode_func_eval, ode_step, rk_step, rollout  # noqa: F401
 from .workloads import (chain_edges, cylinder_flow_mesh, node_mask, synthetic_velocity, tet_grid_edges,  # noqa: F401
                         val_mask)
 from .strategies import (DerivativeTraining, MultipleShooting, SolverTraining, get_delta, init_train_step,  # noqa: F401

@@ -26,6 +26,15 @@ def allreduce_mean_(flat_grads: torch.Tensor, world: int | None = None):
     return flat_grads
 
 
+def allreduce_sum_(*tensors):
+    """In-place SUM over ranks: loss and gradient of a MultipleShooting step whose intervals are sharded over
+    processes (shooting.shard_intervals) - every interval contributes exactly once."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return tensors
+
+
 def allreduce_normaliser_(state: torch.Tensor, prev: torch.Tensor):
     """Online-normaliser state [sum | sum_sq | count | num_acc] after a step in which every rank
     accumulated its own window on top of the common `prev`: new = prev + sum_r (state_r - prev)."""

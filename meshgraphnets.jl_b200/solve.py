@@ -1,13 +1,20 @@
 """Mirror of src/solve.jl: ode_step (:188-219), ode_func_eval (:147-158) and rollout (:42-68) with the
 fixed-step Euler configuration of examples/cylinder_flow/cylinder_flow.jl:79-84.  The adaptive
-Tsit5 driver itself is OrdinaryDiffEq's (out of scope); tsit5_step below restates one explicit
-Tsit5 step so that the 6-RHS-evaluations-per-step workload of config 3 can be timed."""
+Tsit5 driver itself is OrdinaryDiffEq's (out of scope); the fixed-step tableaus of shooting.RK_TABLEAUS restate
+one explicit step so that the 6-RHS-evaluations-per-step workload of config 3 can be run and timed.
+
+Every arithmetic operation - inflow overwrite, normalisers, model, inverse_data, val_mask, the Runge-Kutta
+combinations - is a libmgn_b200 kernel that only enqueues on the current stream, so a whole rollout can be captured
+once and replayed as ONE CUDA graph (CapturedRollout): no host round trip per stage."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
 from .graph import build_graph
+from .shooting import RK_TABLEAUS, DeviceAlgebra
+
+_alg = DeviceAlgebra()
 
 
 def ode_step(x, p, t):
@@ -27,7 +34,11 @@ def ode_step(x, p, t):
         d = meta["features"][tf]["dim"]
         mgn.o_norm[tf].inverse(output[:, col:col + d].contiguous(), out=buf, col=col)
         col += d
-    return buf * val_mask
+    return _alg.mul(buf, val_mask)
+
+
+def _inflow_u8(inflow_mask):
+    return inflow_mask if inflow_mask.dtype == torch.uint8 else inflow_mask.to(torch.uint8)
 
 
 def ode_func_eval(x, p, t):
@@ -37,10 +48,42 @@ def ode_func_eval(x, p, t):
     if inflow_mask is not None:
         # floor(Int, t / saves_dt) + 1 with Float32 t and saves_dt (0-based here)
         idx = int(np.floor(np.float32(t) / np.float32(saves_dt)))
-        cur = torch.cat([data[f][idx] for f in target_fields], dim=1)
-        x.copy_(torch.where(inflow_mask, cur, x))  # in place: the reference mutates the solver state
+        cur = torch.cat([data[f][idx] for f in target_fields], dim=1) if len(target_fields) > 1 \
+            else data[target_fields[0]][idx]
+        # in place: the reference mutates the solver state
+        x.copy_(_alg.overwrite(x, cur.contiguous(), _inflow_u8(inflow_mask)))
     return ode_step(x, (mgn, ps, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats,
                         senders, receivers, val_mask), t)
+
+
+def rk_step(f, x, t, dt, solver="euler"):
+    """One fixed step of an explicit Runge-Kutta method (shooting.RK_TABLEAUS) through mgn_ode_lincomb."""
+    c, A, b = RK_TABLEAUS[solver]
+    h = np.float32(dt)
+    ks = [f(x, t)]
+    for ci, a in zip(c, A):
+        xi = _alg.lincomb(x, ks, [h * np.float32(aj) for aj in a])
+        ks.append(f(xi, np.float32(np.float32(t) + np.float32(ci) * h)))
+    return _alg.lincomb(x, ks, [h * np.float32(bi) for bi in b])
+
+
+def euler_step(f, x, t, dt):
+    return rk_step(f, x, t, dt, "euler")
+
+
+def tsit5_step(f, x, t, dt):
+    """One explicit Tsitouras 5(4) step (6 RHS evaluations; the 7th FSAL stage is the next step's
+    first) - the per-step RHS workload of OrdinaryDiffEq.Tsit5 at src/solve.jl:58."""
+    return rk_step(f, x, t, dt, "tsit5")
+
+
+def _rollout_params(mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
+                    receivers, val_mask, inflow_mask, data, saves):
+    inputs = {k: v for k, v in initial_state.items() if k not in target_dict}
+    if inflow_mask is not None:
+        inflow_mask = _inflow_u8(inflow_mask).contiguous()
+    return (mgn, mgn.ps, data, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
+            receivers, val_mask, inflow_mask, saves[1] - saves[0])
 
 
 def rollout(mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
@@ -48,46 +91,48 @@ def rollout(mgn, initial_state, fields, meta, target_fields, target_dict, node_t
     """src/solve.jl:42-68 with ``solve(prob, Euler(); adaptive=false, dt=dt, saveat=saves)``.
     Returns (list of saved states, times)."""
     x = torch.cat([initial_state[f] for f in target_fields], dim=1).clone()
-    inputs = {k: v for k, v in initial_state.items() if k not in target_dict}
-    p = (mgn, mgn.ps, data, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
-         receivers, val_mask, inflow_mask, saves[1] - saves[0])
+    p = _rollout_params(mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
+                        receivers, val_mask, inflow_mask, data, saves)
     sol, ts = [x.clone()], [float(saves[0])]
-    step = euler_step if solver == "euler" else tsit5_step
-    n_steps = len(saves) - 1
-    for i in range(n_steps):
+    for i in range(len(saves) - 1):
         t = np.float32(saves[i])  # tstops = saves: the integrator lands on the save times
-        x = step(lambda xx, tt: ode_func_eval(xx, p, tt), x, t, dt)
+        x = rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), x, t, dt, solver)
         sol.append(x.clone())
         ts.append(float(saves[i + 1]))
     return sol, ts
 
 
-def euler_step(f, x, t, dt):
-    return x + dt * f(x, t)
+class CapturedRollout:
+    """The same rollout captured once as a single CUDA graph and replayed: ``replay(initial_state)`` copies the
+    initial state into the graph's input and returns the saved states (tensors owned by the graph, overwritten by the
+    next replay).  Normaliser statistics must not change between capture and replay (they are read on the device,
+    so accumulated statistics ARE seen; only the accumulate branch itself is skipped once max_acc is reached)."""
 
+    def __init__(self, mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
+                 receivers, val_mask, inflow_mask, data, start, stop, dt, saves, solver="euler"):
+        self.target_fields = list(target_fields)
+        self.x0 = torch.cat([initial_state[f] for f in target_fields], dim=1).clone()
+        args = (mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders, receivers,
+                val_mask, inflow_mask, data, saves)
+        p = _rollout_params(*args)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):             # warm-up: allocations and first-use scratch happen outside capture
+            for _ in range(2):
+                rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), self.x0.clone(), np.float32(saves[0]), dt, solver)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            x = self.x0.clone()
+            self.sol = [x.clone()]
+            for i in range(len(saves) - 1):
+                x = rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), x, np.float32(saves[i]), dt, solver)
+                self.sol.append(x.clone())
+        self.ts = [float(s) for s in saves]
 
-_TSIT5_C = (0.161, 0.327, 0.9, 0.9800255409045097, 1.0)
-_TSIT5_A = (
-    (0.161,),
-    (-0.008480655492356989, 0.335480655492357),
-    (2.8971530571054935, -6.359448489975075, 4.3622954328695815),
-    (5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525),
-    (5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383),
-)
-_TSIT5_B = (0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
-            2.324710524099774)
-
-
-def tsit5_step(f, x, t, dt):
-    """One explicit Tsitouras 5(4) step (6 RHS evaluations; the 7th FSAL stage is the next step's
-    first) - the per-step RHS workload of OrdinaryDiffEq.Tsit5 at src/solve.jl:58."""
-    k = [f(x, t)]
-    for c, a in zip(_TSIT5_C, _TSIT5_A):
-        xi = x
-        for aj, kj in zip(a, k):
-            xi = xi + (dt * aj) * kj
-        k.append(f(xi, t + c * dt))
-    out = x
-    for bj, kj in zip(_TSIT5_B, k):
-        out = out + (dt * bj) * kj
-    return out
+    def replay(self, initial_state=None):
+        if initial_state is not None:
+            self.x0.copy_(torch.cat([initial_state[f] for f in self.target_fields], dim=1))
+        self.graph.replay()
+        return self.sol, self.ts

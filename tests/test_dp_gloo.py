@@ -82,6 +82,51 @@ def test_dp2_gradient_is_mean_of_window_gradients():
     assert state[9] == serial.num_acc
 
 
+def _shooting_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+        import mgn_pkg
+        from test_oracle_solver import _problem as shooting_problem
+        from test_shooting_host import _run
+        pkg = mgn_pkg.pkg
+        cfg, p, make, _, N = shooting_problem(seed=3, T=9)
+        kw = dict(tstart=0.0, dt=0.01, tstop=0.08, interval_size=3, continuity_term=10, solver="euler", n_sub=1)
+        owned = pkg.shard_intervals(len(pkg.shooting_ranges(9, 3)), rank, world)
+        g, loss, _, _ = _run(pkg, make, p, N, owned=owned, **kw)
+        tg, tl = torch.from_numpy(g.copy()), torch.tensor([loss], dtype=torch.float64)
+        pkg.allreduce_sum_(tg, tl)
+        q.put((owned, tg.numpy() if rank == 0 else None, float(tl[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_multiple_shooting_intervals_sharded_over_2_ranks():
+    """shooting intervals are independent solves; sharded over two gloo ranks and SUM-reduced, loss and
+    gradient equal the unsharded step (the engine runs on the CPU test doubles of tests/test_shooting_host.py)."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shooting_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(o for o, _, _ in res) == [[0, 2], [1, 3]]
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import mgn_oracle_solver as sol
+    from test_oracle_solver import _problem as shooting_problem
+    cfg, p, make, _, N = shooting_problem(seed=3, T=9)
+    g_ref, loss_ref, _ = sol.train_step_multiple_shooting(make(p), 0.0, 0.01, 0.08, 3, 10, "euler", 1)
+    g = next(f for _, f, _ in res if f is not None)
+    assert all(abs(l - loss_ref) < 1e-11 * abs(loss_ref) for _, _, l in res)
+    assert np.allclose(g, g_ref, rtol=1e-9, atol=1e-12 * np.abs(g_ref).max())
+
+
 def test_shard_windows_properties():
     sys.path[:0] = [ROOT]
     import mgn_pkg

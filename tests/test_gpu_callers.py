@@ -143,3 +143,32 @@ def test_50_step_euler_rollout_matches_oracle(pkg, mode, tol):
     assert len(sol) == 51 and torch.isfinite(sol[-1]).all()
     for i in (1, 10, 25, 50):
         assert rel(sol[i].cpu().numpy() - x0, sol_o[i] - x0) < tol, i
+
+
+@pytest.mark.parametrize("solver", ["euler", "tsit5"])
+def test_captured_rollout_replays_the_eager_rollout(pkg, solver):
+    """the whole rollout (inflow overwrite, build_graph normalisers, model, inverse_data, val_mask and
+    the Runge-Kutta combinations of every step) captured once as ONE CUDA graph; replays are bitwise identical to the
+    eager rollout, also from a different initial state."""
+    data_h, data, meta, mgn, (node_type, senders, receivers, ef), o = _setup(pkg, T=12, mode=1)
+    x0 = data_h["velocity"][0]
+    for n_g, x in ((mgn.n_norm["velocity"], x0), (mgn.e_norm, o["ef"]),
+                   (mgn.o_norm["velocity"], (data_h["velocity"][1] - x0) / np.float32(0.01))):
+        n_g(dev(x))
+        n_g.max_acc = 0.0
+    vm = dev(orc.val_mask(o["nt"], [0, 5], 2))
+    inflow = dev(np.repeat((o["nt"] == 1)[:, None], 2, axis=1))
+    saves = [np.float32(0.01) * i for i in range(11)]
+    args = (mgn, {"velocity": dev(x0)}, ["velocity"], meta, ["velocity"], {"velocity": 2}, node_type, ef, senders,
+            receivers, vm, inflow, data, 0.0, 0.1, 0.01, saves)
+    sol, ts = pkg.rollout(*args, solver=solver)
+    cap = pkg.CapturedRollout(*args, solver=solver)
+    for _ in range(2):
+        sol_g, ts_g = cap.replay()
+        assert ts_g == ts and len(sol_g) == 11
+        assert all(torch.equal(a, b) for a, b in zip(sol, sol_g))
+    x1 = {"velocity": dev(data_h["velocity"][1])}
+    sol2, _ = pkg.rollout(mgn, x1, *args[2:], solver=solver)
+    sol2_g, _ = cap.replay(x1)
+    assert all(torch.equal(a, b) for a, b in zip(sol2, sol2_g))
+    assert not torch.equal(sol2_g[-1], sol[-1])

@@ -4,9 +4,10 @@ SEQUENTIAL fp64 oracle (oracle/mgn_oracle_solver.py); the new C-ABI kernels agai
 (100k-node chain, multiple shooting) bf16 against fp32 mode.
 
 Tolerances (relative L2 unless stated), fp32 mode / bf16 tensor-core mode against the fp64 oracle:
-  predictions (state change over an interval)   1e-3 / 6e-2   (same as the rollout tests)
-  loss                                          1e-3 / 6e-2
-  parameter gradient                            5e-3 / 0.2    (a chain of up to 12 pulled-back RHS evaluations)
+  predictions (state change over an interval)   1e-3          (same as the rollout tests)
+  loss                                          1e-4 / 2e-2   (observed 3e-6 / 5e-3)
+  parameter gradient                            2e-3 / 0.15   (observed 3e-4 / 4.5e-2: up to 12 pulled-back RHS evaluations)
+  parameter gradient, one Tsit5 step            1e-2          (observed 3e-3, see below)
 
 Tsit5 is only compared over ONE step per interval: the exact gradient of a multi-step fixed-step Tsit5 solve of a
 ReLU network is ill-conditioned in single precision - the tableau's large cancelling coefficients (a_52 = -11.7,
@@ -61,8 +62,8 @@ def _frozen_problem(pkg, mode, T=9, mps=3):
 
 
 @pytest.mark.parametrize("mode,solver,n_sub,isz,tols", [
-    (0, "euler", 1, 4, (1e-3, 1e-3, 5e-3)), (0, "euler", 2, 4, (1e-3, 1e-3, 5e-3)), (0, "rk4", 1, 4, (1e-3, 1e-3, 5e-3)),
-    (0, "tsit5", 1, 2, (1e-3, 1e-3, 1e-2)), (1, "euler", 1, 4, (6e-2, 6e-2, 0.2)), (1, "rk4", 1, 4, (6e-2, 6e-2, 0.2))])
+    (0, "euler", 1, 4, (1e-3, 1e-4, 2e-3)), (0, "euler", 2, 4, (1e-3, 1e-4, 2e-3)), (0, "rk4", 1, 4, (1e-3, 1e-4, 2e-3)),
+    (0, "tsit5", 1, 2, (1e-3, 1e-4, 1e-2)), (1, "euler", 1, 4, (6e-2, 2e-2, 0.15)), (1, "rk4", 1, 4, (6e-2, 2e-2, 0.15))])
 def test_multiple_shooting_step_matches_sequential_oracle(pkg, mode, solver, n_sub, isz, tols):
     """Intervals of 4, 4 and 2 observations (7 intervals of 2 for Tsit5) solved in lock-step on one block-diagonal
     graph vs the oracle's interval-by-interval solves: loss (incl. the continuity terms) and the parameter gradient."""
@@ -82,8 +83,8 @@ def test_multiple_shooting_step_matches_sequential_oracle(pkg, mode, solver, n_s
     assert torch.equal(gs, gs2) and torch.equal(loss, loss2)
 
 
-@pytest.mark.parametrize("mode,solver,tstop,tols", [(0, "euler", 0.04, (1e-3, 5e-3)), (0, "rk4", 0.04, (1e-3, 5e-3)),
-                                                     (0, "tsit5", 0.01, (1e-3, 1e-2)), (1, "euler", 0.04, (6e-2, 0.2))])
+@pytest.mark.parametrize("mode,solver,tstop,tols", [(0, "euler", 0.04, (1e-4, 2e-3)), (0, "rk4", 0.04, (1e-4, 2e-3)),
+                                                     (0, "tsit5", 0.01, (1e-4, 1e-2)), (1, "euler", 0.04, (2e-2, 0.15))])
 def test_solver_training_step_matches_oracle(pkg, mode, solver, tstop, tols):
     t, rhs_o, o, mgn = _frozen_problem(pkg, mode, T=6)
     strat = pkg.SolverTraining(0.0, 0.01, tstop, solver)

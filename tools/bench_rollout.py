@@ -74,7 +74,23 @@ def main():
         g.replay()
     e1.record()
     torch.cuda.synchronize()
-    print(json.dumps({"workload": "cylinder_flow_rollout_50_steps", "nodes": N, "edges": E, "mps": 15,
+    # the whole 50-step rollout as ONE CUDA graph (CapturedRollout)
+    args = (mgn, init, ["velocity"], meta, ["velocity"], {"velocity": 2}, node_type, ef, senders, receivers, val_mask,
+            inflow, data, 0.0, 0.5, 0.01, saves)
+    captured = {}
+    for solver in ("euler", "tsit5"):
+        cap = pkg.CapturedRollout(*args, solver=solver)
+        cap.replay()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            cap.replay()
+        c1.record()
+        torch.cuda.synchronize()
+        captured[solver] = c0.elapsed_time(c1) / 3
+    print(json.dumps({"workload": "cylinder_flow_rollout_50_steps", "euler_50_steps_one_graph_ms": captured["euler"],
+                      "tsit5_50_steps_one_graph_ms": captured["tsit5"], "nodes": N, "edges": E, "mps": 15,
                       "mode": "bf16" if mode == pkg.COMPUTE_BF16 else "fp32",
                       "euler_50_steps_ms": ms_euler, "tsit5_50_steps_ms": ms_tsit,
                       "rhs_ms_plain": ms_euler / 50, "rhs_ms_cuda_graph": e0.elapsed_time(e1) / 50,
