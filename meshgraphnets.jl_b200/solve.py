@@ -115,6 +115,7 @@ class CapturedRollout:
         args = (mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders, receivers,
                 val_mask, inflow_mask, data, saves)
         p = _rollout_params(*args)
+        self._keep = p      # the graph holds raw addresses: every tensor it reads must outlive it (e.g. the uint8 mask)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):             # warm-up: allocations and first-use scratch happen outside capture
