@@ -3,7 +3,13 @@
 mirror): CylinderFlow-shaped mesh, 15 MP steps, tsteps = 0:0.01:0.49 (50 observations), interval_size 6 -> 10 shooting
 intervals.  Times one train_step (lock-step solve + reverse sweep) with CUDA events and, for comparison, the same step
 with the intervals solved one after the other (the reference's order, strategies.jl:349-362) through the same
-kernels.  Prints one JSON line per configuration."""
+kernels.  Prints one JSON line per configuration.
+
+Under torchrun (WORLD_SIZE > 1, one process per GPU) the shooting intervals of a longer trajectory (`--obs`, default 200
+observations -> 40 intervals) are sharded over the ranks (shooting.shard_intervals), loss and gradient are SUM-all-reduced
+over NCCL, and the time is the max over ranks:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29571 \
+        tools/bench_shooting.py bf16 --sharded"""
 import json
 import os
 import sys
@@ -30,8 +36,73 @@ def timed(fn, reps):
     return e0.elapsed_time(e1) / reps, out
 
 
+def sharded(mode):
+    """Interval-sharded MultipleShooting step over the ranks of a torchrun job."""
+    import torch.distributed as dist
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    T = int(sys.argv[sys.argv.index("--obs") + 1]) if "--obs" in sys.argv else 200
+    pos, cells, nt = pkg.cylinder_flow_mesh(65, 29)
+    vel = pkg.synthetic_velocity(pos, T + 1, seed=1)
+    data_h = {"node_type": nt.reshape(1, -1, 1), "mesh_pos": pos[None], "cells": cells[None]}
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0, device=dev)
+    model, ps, st = pkg.build_model(9, 2, 2, 15, 128, 2, device=dev, compute_mode=mode)
+    mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOnline(3, dev),
+                           {"velocity": pkg.NormaliserOnline(2, dev), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
+                           {"velocity": pkg.NormaliserOnline(2, dev)})
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    data = {"velocity": to(vel[:T]), "target|velocity": to(vel[1:T + 1]), "node_type": to(nt.reshape(1, -1, 1).astype(np.int32))}
+    for f in range(3):
+        mgn.n_norm["velocity"](data["velocity"][f])
+        mgn.o_norm["velocity"]((data["velocity"][f + 1] - data["velocity"][f]) / 0.01)
+    mgn.e_norm(ef)
+    meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}}, "target_features": ["velocity"]}
+    vm = to(pkg.val_mask(nt, [0, 5], 2))
+    t = (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders, receivers, 1, None, vm)
+    tstop = 0.01 * (T - 1)
+    n_int = len(pkg.shooting_ranges(T, 6))
+    strat = pkg.MultipleShooting(0.0, 0.01, tstop, "euler", interval_size=6, continuity_term=100, rank=rank, world=world)
+    tt = pkg.init_train_step(strat, t, None)
+
+    def step():
+        (gs,), loss = pkg.train_step(strat, tt)
+        pkg.allreduce_sum_(gs, loss)
+        return gs, loss
+    step()
+    times = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gs, loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times.append(float(ms.cpu()))
+    if rank == 0:
+        ms = float(np.median(times))
+        E = int(senders.shape[0])
+        print(json.dumps({"workload": "cylinder_flow_multiple_shooting_step_sharded", "n_gpus": world, "observations": T,
+                          "intervals": n_int, "intervals_per_rank": len(pkg.shard_intervals(n_int, 0, world)),
+                          "solver": "euler", "mode": "bf16" if mode == pkg.COMPUTE_BF16 else "fp32",
+                          "ms_per_train_step": ms, "scaling": "strong",
+                          "mp_step_edges_per_sec_train_equiv": (5 + 5 / 3) * n_int * E * 15 / (ms * 1e-3),
+                          "loss": float(loss.cpu()), "grad_norm": float(gs.norm().cpu())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     mode = pkg.COMPUTE_BF16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else pkg.COMPUTE_FP32
+    if "--sharded" in sys.argv:
+        return sharded(mode)
     dev = torch.device("cuda", 0)
     pos, cells, nt = pkg.cylinder_flow_mesh(65, 29)
     T = 50
