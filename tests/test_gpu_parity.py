@@ -101,28 +101,31 @@ def _problem(nx, ny, D, mps, node_in=9, edge_in=3, seed=0, hidden=2):
                                                 (6, 4, 128, 2, 1)])
 def test_step_matches_oracle_fp32(pkg, nx, ny, D, mps, hidden):
     """fp32 CUDA-core mode vs the fp64 oracle: loss, output, every parameter gradient and the
-    gradient w.r.t. the node features.  Tolerance 2e-4 relative L2 (fp32 accumulation order)."""
+    gradient w.r.t. the node features.  Tolerances (relative L2): output 5e-6, loss 2e-6, gradients 1e-5, any single
+    parameter tensor 2e-5 - about ten times what is observed on B200 (output 8e-7, gradients 2.4e-7, d/d nf 6.6e-7,
+    worst tensor 6e-7: `tools/debug_fp32_accuracy.py`), which is also what the numpy fp32 run of the oracle shows
+    against its fp64 run: the kernels lose nothing beyond fp32 arithmetic itself."""
     cfg, ps, nf, ef, s, r, tgt, mask, _ = _problem(nx, ny, D, mps, hidden=hidden)
     g_o, loss_o, out_o, dnf_o = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
     model = pkg.Model(cfg.node_in, cfg.edge_in, 2, mps, D, hidden)
     graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
     out = model.forward(graph, dev(ps), training=True)
-    assert rel(out.cpu().numpy(), out_o) < 2e-5
+    assert rel(out.cpu().numpy(), out_o) < 5e-6
     mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
     (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
-    assert abs(float(loss.cpu()) - loss_o) < 2e-5 * abs(loss_o)
-    assert rel(gs.cpu().numpy(), g_o) < 2e-4
+    assert abs(float(loss.cpu()) - loss_o) < 2e-6 * abs(loss_o)
+    assert rel(gs.cpu().numpy(), g_o) < 1e-5
     # per-tensor check so that a tiny tensor (a bias) cannot hide in the global norm
     for name, off, rows, cols in model.param_layout():
         ref = g_o[off:off + rows * cols]
         got = gs[off:off + rows * cols].cpu().numpy()
-        assert np.linalg.norm(got - ref) <= 5e-4 * np.linalg.norm(ref) + 1e-7 * np.linalg.norm(g_o), name
+        assert np.linalg.norm(got - ref) <= 2e-5 * np.linalg.norm(ref) + 1e-7 * np.linalg.norm(g_o), name
     # VJP w.r.t. the node features (NeuralODE adjoint, SURVEY 8 a16)
     out2 = model.forward(graph, dev(ps), training=True)
     _, dout_o = orc.loss_and_dout(out_o, tgt.astype(np.float64), mask)
     dps, dnf = model.backward(graph, dev(ps), dev(dout_o.astype(np.float32)), want_dnf=True)
-    assert rel(dnf.cpu().numpy(), dnf_o) < 2e-4
-    assert rel(dps.cpu().numpy(), g_o) < 2e-4
+    assert rel(dnf.cpu().numpy(), dnf_o) < 1e-5
+    assert rel(dps.cpu().numpy(), g_o) < 1e-5
     assert torch.equal(out, out2)  # deterministic: no atomics anywhere on the path
 
 
@@ -148,17 +151,17 @@ def test_edge_order_permutation_invariance(pkg):
 
 
 def test_cylinder_flow_full_size_fp32(pkg):
-    """BASELINE configs[1] at full size (N=1885, E=10936, D=128, mps=15) against the fp32 numpy
-    oracle (the fp64 one takes too long for the CPU suite budget); tolerance 1e-3 on gradients -
-    both sides are fp32 with different summation orders through 15 residual blocks."""
+    """BASELINE configs[1] at full size (N=1885, E=10936, D=128, mps=15) against the fp64 oracle: loss 1e-5,
+    gradient 2e-5 (fp32 summation-order differences through 15 residual blocks; the numpy fp32 run of the oracle sits
+    at 3e-7 from its fp64 run)."""
     cfg, ps, nf, ef, s, r, tgt, mask, _ = _problem(65, 29, 128, 15)
     g_o, loss_o, out_o, _ = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
     model = pkg.Model(9, 3, 2, 15, 128, 2)
     graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
     mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
     (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
-    assert abs(float(loss.cpu()) - loss_o) < 1e-4 * abs(loss_o)
-    assert rel(gs.cpu().numpy(), g_o) < 1e-3
+    assert abs(float(loss.cpu()) - loss_o) < 1e-5 * abs(loss_o)
+    assert rel(gs.cpu().numpy(), g_o) < 2e-5
 
 
 # ------------------------------------------------------------------ loss / Adam / normalisers
