@@ -22,17 +22,28 @@ namespace mgn {
 namespace tc {
 namespace {
 
-constexpr int kRing = 4;
-constexpr int kThreads = 192;  // warps 0-3: epilogue, warp 4: producer, warp 5: MMA issue
-constexpr uint32_t kSmemRing = 0;
-constexpr uint32_t kSmemH = kRing * kTileB;                  // 2 tiles: hidden activation / xhat
-constexpr uint32_t kSmemBias = kSmemH + 2 * kTileB;          // [kMaxLayers][128] fp32
-constexpr uint32_t kSmemLn = kSmemBias + kMaxLayers * 512;   // scale[128], bias[128]
-constexpr uint32_t kSmemRp = kSmemLn + 1024;                 // tile-local CSR row pointer, 132 ints
-constexpr uint32_t kSmemBar = kSmemRp + 132 * 4;             // full[4], empty[4], acc_full, epi_done
-constexpr uint32_t kSmemTmem = kSmemBar + 16 * 8;
-constexpr uint32_t kSmemTotal = kSmemTmem + 16;
-constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;          // slack for the 1024 B alignment
+// Thread layout, EW = number of epilogue warps (4 or 8): warps 0..EW-1 epilogue, warp EW producer, warp EW+1 MMA
+// issue.  With EW = 8 two threads share a tile row: thread (row, half) owns the 64 accumulator columns of its half
+// (warps w and w+4 both address TMEM lanes 32*(w%4)..+31), which halves the serial length of every Dense / LayerNorm
+// epilogue and doubles the loads in flight of the copy-out.
+// Operand ring, RING = number of 16 KB slots: 4 when two CTAs share an SM (large graphs: the other CTA hides the
+// staging latency), 10 when the graph has no more tiles than the chip has SMs (one CTA per SM anyway): then ten of the
+// twelve layer-0 tiles of an edge MLP (6 gathered A tiles + 6 weight tiles) are in flight at once and the first
+// accumulator is ready after one gather latency instead of six.
+template <int RING>
+struct Lay {
+  static constexpr uint32_t kRing = 0;
+  static constexpr uint32_t kH = RING * kTileB;                // 2 tiles: hidden activation / xhat
+  static constexpr uint32_t kBias = kH + 2 * kTileB;           // [kMaxLayers][128] fp32
+  static constexpr uint32_t kLn = kBias + kMaxLayers * 512;    // scale[128], bias[128]
+  static constexpr uint32_t kRp = kLn + 1024;                  // tile-local CSR row pointer, 132 ints
+  static constexpr uint32_t kStat = kRp + 132 * 4;             // EW = 8: LayerNorm partial sums [2 halves][128 rows] float2
+  static constexpr uint32_t kBar = kStat + 2 * 128 * 8;        // full[RING], empty[RING], acc_full, epi_done
+  static constexpr uint32_t kTmem = kBar + (2 * RING + 2) * 8;
+  static constexpr uint32_t kTotal = kTmem + 16;
+  static constexpr uint32_t kLaunch = kTotal + 1024;           // slack for the 1024 B alignment
+};
+constexpr int kRingShared = 4, kRingDeep = 10;
 
 // ---------------------------------------------------------------------------------------------------
 // Weight packing: fp32 Julia-layout weights -> bf16 128B-swizzled K-major image tiles.
@@ -85,7 +96,16 @@ __device__ __forceinline__ void tile_rows(const FwdParams& p, int tile, int64_t&
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p) {
+template <int EW, int RING>
+__global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) mlp_fwd_kernel(const FwdParams p) {
+  using L_ = Lay<RING>;
+  constexpr int kRing = RING;
+  constexpr uint32_t kSmemRing = L_::kRing, kSmemH = L_::kH, kSmemBias = L_::kBias, kSmemLn = L_::kLn, kSmemRp = L_::kRp,
+                     kSmemStat = L_::kStat, kSmemBar = L_::kBar, kSmemTmem = L_::kTmem;
+  constexpr int kThreads = 32 * (EW + 2);
+  constexpr int kEpi = 32 * EW;        // epilogue threads
+  constexpr int kHalves = EW / 4;      // threads per tile row
+  constexpr int kWarpP = EW, kWarpM = EW + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
@@ -116,16 +136,16 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(epi_done, 128);
+    mbar_init(epi_done, kEpi);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 128);
+  if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 128);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kWarpP) {
     // ================================ producer ================================
     uint32_t it = 0;
     int tn = 0;
@@ -227,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kWarpM) {
     // ================================ MMA issue ================================
     if (lane == 0) {
       uint32_t it = 0, epi_par = 0;
@@ -272,12 +292,14 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
       }
     }
   } else {
-    // ================================ epilogue (thread == row) ================================
+    // ================================ epilogue (thread == (row, column half)) ================================
     uint32_t acc_par = 0;
     bool store_pending = false;
     int tn = 0;
-    const int row = tid;  // 0..127
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row = tid & 127, half = tid >> 7;  // half == 0 when EW == 4
+    const int c_lo = half * (4 / kHalves), c_hi = c_lo + 4 / kHalves;  // 32-column accumulator chunks of this thread
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float2* stat_s = reinterpret_cast<float2*>(smem + kSmemStat);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int64_t row0;
       int cnt;
@@ -291,10 +313,10 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         const bool last = l == L - 1;
         if (last && p.fin_mode == FIN_LINEAR) {
           float v[16];
-          tmem_ld16(t_lane, v);
+          if (half == 0) tmem_ld16(t_lane, v);  // warp-uniform: a warp belongs to one half
           tc_fence_before();
           mbar_arrive(epi_done);
-          if (row < cnt)
+          if (half == 0 && row < cnt)
             for (int j = 0; j < p.out_dim; ++j) p.out[(row0 + row) * p.out_dim + j] = v[j] + bias_s[l * 128 + j];
           continue;
         }
@@ -304,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
           bulk_wait_read0();
           store_pending = false;
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpi);
         if (l == 0 && p.fin_mode == FIN_LN_RESID_AGG) {
           // tile-local CSR row pointer -> shared memory (read by the aggregation after two more barriers)
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
@@ -317,32 +339,43 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         }
         // residual rows of the first copy-out batch: issued now so that their latency hides behind the LayerNorm
         // residual rows are fetched 4 per thread at a time into one half of r0/r1 while the other half is consumed
-        float4 r0[8], r1[8];
+        constexpr int RG = kEpi / 16;  // row groups of the copy-out (8 or 16)
+        constexpr int U = 32 / RG;     // rows per thread and 32-row batch (4 or 2)
+        float4 r0[2 * U], r1[2 * U];
         const int cc = tid & 15, rg = tid >> 4;
         const bool resid = p.fin_mode != FIN_LN && p.lat_in != nullptr;
         const bool write_lat = p.lat_out != nullptr;  // false: only the aggregation is wanted (last MP step's edge latent)
-        auto issue_residual = [&](int k, int h) {  // batch k covers rows 32k + rg + 8u
+        auto issue_residual = [&](int k, int h) {  // batch k covers rows 32k + rg + RG*u
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = 32 * k + rg + 8 * u;
-            r0[4 * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[4 * h + u] = r0[4 * h + u];
+          for (int u = 0; u < U; ++u) {
+            const int i = 32 * k + rg + RG * u;
+            r0[U * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            r1[U * h + u] = r0[U * h + u];
             if (resid && i < cnt) {
               const int64_t o = (row0 + i) * 128 + cc * 8;
-              r0[4 * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o);
-              r1[4 * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+              r0[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o);
+              r1[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
             }
           }
         };
         float mean = 0.f, rstd = 1.f;
         if (last) {  // LayerNorm statistics in ONE extra pass over TMEM: sums of the data shifted by the row's first
                      // element (the shifted-data formula keeps the fp32 variance accurate), biased variance
-          float s = 0.f, q = 0.f, shift = 0.f;
+          // sums over the left and the right 64 columns separately, then added: the same arithmetic for both thread
+          // layouts (mirrored by oracle/mgn_oracle_bf16.py)
+          float s = 0.f, q = 0.f, s_lo = 0.f, q_lo = 0.f, shift = 0.f;
+          if (kHalves == 2) shift = tmem_ld1(t_lane) + bias_s[l * 128];  // both halves shift by the row's first element
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = c_lo; c < c_hi; ++c) {
             float v[32];
             tmem_ld32(t_lane + c * 32, v);
-            if (c == 0) shift = v[0] + bias_s[l * 128];
+            if (kHalves == 1 && c == 0) shift = v[0] + bias_s[l * 128];
+            if (kHalves == 1 && c == 2) {
+              s_lo = s;
+              q_lo = q;
+              s = 0.f;
+              q = 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float d = v[j] + bias_s[l * 128 + c * 32 + j] - shift;
@@ -350,14 +383,24 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
               q = fmaf(d, d, q);
             }
           }
+          if (kHalves == 2) {
+            stat_s[half * 128 + row] = make_float2(s, q);
+            named_bar_sync(1, kEpi);
+            const float2 a = stat_s[row], b = stat_s[128 + row];
+            s = a.x + b.x;
+            q = a.y + b.y;
+          } else {
+            s = s_lo + s;
+            q = q_lo + q;
+          }
           const float ms = s * (1.f / 128.f);
           mean = shift + ms;
           q = fmaxf(q * (1.f / 128.f) - ms * ms, 0.f) * 128.f;
           rstd = 1.f / sqrtf(q * (1.f / 128.f) + p.eps);
-          if (p.save_rstd && row < cnt) p.save_rstd[row0 + row] = rstd;
+          if (p.save_rstd && row < cnt && half == 0) p.save_rstd[row0 + row] = rstd;
         }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           float v[32];
           tmem_ld32(t_lane + c * 32, v);
           uint32_t w[16];
@@ -384,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         __nv_bfloat16* save = last ? p.save_xhat : p.save_h[l];
         if (!last) {
           if (save) {
-            named_bar_sync(1, 128);
+            named_bar_sync(1, kEpi);
             if (tid == 0) {
               bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
               bulk_commit();
@@ -396,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         }
         // ---- last layer: TMEM is drained -> the MMA warp may start the next tile
         mbar_arrive(epi_done);
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpi);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: LayerNorm done, xhat staged
         if (save && tid == 0) {
           bulk_s2g(reinterpret_cast<uint8_t*>(save) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
@@ -413,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         if (p.fin_mode == FIN_LN_RESID_AGG) {
           const int n0 = rp_s[130], nn = rp_s[131];
           __nv_bfloat16* agg = p.agg_bf16 + (int64_t)n0 * 128;
-          segsum_tile<true>(s_h, s_base + kSmemRp, nn, tid, ln_s, ln_s + 128,
+          segsum_tile<true, (EW == 8 ? 4 : 3)>(s_h, s_base + kSmemRp, nn, tid, ln_s, ln_s + 128,
                             [&](int v, int col0, const float (&a)[8]) {
                               uint4 o;
                               o.x = pack_bf16x2(a[0], a[1]);
@@ -432,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
             bulk_wait_read0();
             store_pending = false;
           }
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpi);
         }
         // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced), four batches of
         //      32 rows, the residual rows of batch k+1 in flight while batch k is written
@@ -448,8 +491,8 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
             const int h = k & 1;
             if (k + 1 < 4) issue_residual(k + 1, h ^ 1);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int i = 32 * k + rg + 8 * u;
+            for (int u = 0; u < U; ++u) {
+              const int i = 32 * k + rg + RG * u;
               if (i >= cnt) {
                 if (img_out) st_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7), 0u, 0u, 0u, 0u);
                 continue;
@@ -463,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
                 m[2 * j] = fmaf(__low2float(hh), sc[2 * j], bi[2 * j]);
                 m[2 * j + 1] = fmaf(__high2float(hh), sc[2 * j + 1], bi[2 * j + 1]);
               }
-              const float4 a0 = r0[4 * h + u], a1 = r1[4 * h + u];
+              const float4 a0 = r0[U * h + u], a1 = r1[U * h + u];
               m[0] += a0.x; m[1] += a0.y; m[2] += a0.z; m[3] += a0.w;
               m[4] += a1.x; m[5] += a1.y; m[6] += a1.z; m[7] += a1.w;
               const int64_t o = (row0 + i) * 128 + cc * 8;
@@ -481,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
         }
         if (img_out) {
           fence_proxy_async();
-          named_bar_sync(1, 128);
+          named_bar_sync(1, kEpi);
           if (tid == 0) {
             bulk_s2g(reinterpret_cast<uint8_t*>(p.lat_img_out) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
             bulk_commit();
@@ -495,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, 2) mlp_fwd_kernel(const FwdParams p)
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 128);
+  if (warp == kWarpM) tmem_dealloc(tmem, 128);
 }
 
 }  // namespace
@@ -507,12 +550,28 @@ cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat
   return cudaGetLastError();
 }
 
+// Epilogue warps per CTA: 8 (two threads per tile row) unless MGN_FWD_EPI_WARPS=4 selects the one-thread-per-row layout.
+static int fwd_epilogue_warps() {
+  static int ew = 0;
+  if (ew == 0) {
+    const char* e = getenv("MGN_FWD_EPI_WARPS");
+    ew = (e && atoi(e) == 4) ? 4 : 8;
+  }
+  return ew;
+}
+
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
   if (p.n_tiles == 0) return cudaSuccess;
   static bool configured = false;
   static int n_sm = 148;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLaunch);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void* f, uint32_t bytes) {
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    };
+    set((const void*)mlp_fwd_kernel<4, kRingShared>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingShared>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingDeep>, Lay<kRingDeep>::kLaunch);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -531,7 +590,17 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
     }
     q.stagger_ns = grid > n_sm ? (uint32_t)stagger : 0u;
   }
-  mlp_fwd_kernel<<<grid, kThreads, kSmemLaunch, st>>>(q);
+  static int deep_ok = -1;  // MGN_FWD_DEEP_RING=0 disables the deep-ring variant
+  if (deep_ok < 0) {
+    const char* e = getenv("MGN_FWD_DEEP_RING");
+    deep_ok = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  if (fwd_epilogue_warps() == 4)
+    mlp_fwd_kernel<4, kRingShared><<<grid, 32 * 6, Lay<kRingShared>::kLaunch, st>>>(q);
+  else if (deep_ok && p.n_tiles <= n_sm)
+    mlp_fwd_kernel<8, kRingDeep><<<grid, 32 * 10, Lay<kRingDeep>::kLaunch, st>>>(q);
+  else
+    mlp_fwd_kernel<8, kRingShared><<<grid, 32 * 10, Lay<kRingShared>::kLaunch, st>>>(q);
   return cudaGetLastError();
 }
 

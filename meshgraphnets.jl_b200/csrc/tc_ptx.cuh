@@ -173,6 +173,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One fp32 column (lane i of the warp's 32 lanes -> thread i).
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+  uint32_t r;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  return __uint_as_float(r);
+}
+
 // ---- debug trace ----------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
@@ -218,12 +226,13 @@ __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
 // a node are in flight together, then added in order.  kAffine: every element is first mapped to
 // fma(x, scale, bias) (the LayerNorm affine of the message; sc / bi at shared float pointers).
 // flush(v_local, col0, sums[8]) once per node.
-template <bool kAffine, class Flush>
+// kGroupsLog2: the node list is split over 2^kGroupsLog2 thread groups of 16 (3: 128 threads, 4: 256 threads).
+template <bool kAffine, int kGroupsLog2 = 3, class Flush>
 __device__ __forceinline__ void segsum_tile(uint32_t tile, uint32_t rp, int n_nodes, int t, const float* sc_s,
                                             const float* bi_s, Flush flush) {
   const uint32_t chunk = (uint32_t)t & 7u, tsel = ((uint32_t)t >> 3) & 1u;
   const int grp = t >> 4;
-  const int vb = (n_nodes * grp) >> 3, ve = (n_nodes * (grp + 1)) >> 3;
+  const int vb = (n_nodes * grp) >> kGroupsLog2, ve = (n_nodes * (grp + 1)) >> kGroupsLog2;
   const int col0 = (int)(tsel * 64u + chunk * 8u);
   const uint32_t base = tile + tsel * 16384u;
   float sc[8], bi[8];

@@ -61,16 +61,23 @@ class _Mlp:
         if self.s.ln is None:
             return z
         # LayerNorm statistics exactly as the kernel computes them: one pass, data shifted by the row's first
-        # element, sequential fp32 sums (fused multiply-add for the squares), biased variance
+        # element, sequential fp32 sums (fused multiply-add for the squares) over the left and the right half of the
+        # row separately (two threads share a row), halves added, biased variance
         f = np.float32
         z32 = z.astype(f)
         shift = z32[:, :1]
         d = (z32 - shift).astype(f)
-        ssum = np.zeros(z32.shape[0], f)
-        qsum = np.zeros(z32.shape[0], f)
-        for j in range(z32.shape[1]):
-            ssum = (ssum + d[:, j]).astype(f)
-            qsum = (d[:, j].astype(np.float64) * d[:, j] + qsum).astype(f)
+        half = z32.shape[1] // 2
+        parts = []
+        for lo in (0, half):
+            ssum = np.zeros(z32.shape[0], f)
+            qsum = np.zeros(z32.shape[0], f)
+            for j in range(lo, lo + half):
+                ssum = (ssum + d[:, j]).astype(f)
+                qsum = (d[:, j].astype(np.float64) * d[:, j] + qsum).astype(f)
+            parts.append((ssum, qsum))
+        ssum = (parts[0][0] + parts[1][0]).astype(f)
+        qsum = (parts[0][1] + parts[1][1]).astype(f)
         ms = (ssum * f(1.0 / 128.0)).astype(f)
         mean32 = (shift[:, 0] + ms).astype(f)
         var128 = (np.maximum((qsum * f(1.0 / 128.0)).astype(f) - (ms * ms).astype(f), f(0)) * f(128)).astype(f)
