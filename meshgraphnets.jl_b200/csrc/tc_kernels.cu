@@ -96,16 +96,19 @@ __device__ __forceinline__ void tile_rows(const FwdParams& p, int tile, int64_t&
   }
 }
 
-template <int EW, int RING>
-__global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) mlp_fwd_kernel(const FwdParams p) {
+// NP = producer warps: 1 when two CTAs share an SM, 4 in the deep-ring variant (each warp stages 32 of the 128 rows, so
+// the gather instructions of a tile are issued four times faster - what bounds the latency of a single tile).
+template <int EW, int RING, int NP>
+__global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 1) mlp_fwd_kernel(const FwdParams p) {
   using L_ = Lay<RING>;
   constexpr int kRing = RING;
   constexpr uint32_t kSmemRing = L_::kRing, kSmemH = L_::kH, kSmemBias = L_::kBias, kSmemLn = L_::kLn, kSmemRp = L_::kRp,
                      kSmemStat = L_::kStat, kSmemBar = L_::kBar, kSmemTmem = L_::kTmem;
-  constexpr int kThreads = 32 * (EW + 2);
+  constexpr int kThreads = 32 * (EW + NP + 1);
   constexpr int kEpi = 32 * EW;        // epilogue threads
   constexpr int kHalves = EW / 4;      // threads per tile row
-  constexpr int kWarpP = EW, kWarpM = EW + 1;
+  constexpr int kWarpP = EW, kWarpM = EW + NP;
+  constexpr int RPW = 4 / NP;          // 32-row groups staged by one producer warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
     for (int i = tid; i < 256; i += kThreads) ln_s[i] = i < 128 ? p.ln_scale[i] : p.ln_bias[i - 128];
   if (tid == 0) {
     for (int s = 0; s < kRing; ++s) {
-      mbar_init(full_bar(s), 32);
+      mbar_init(full_bar(s), 32 * NP);
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(acc_full, 1);
@@ -145,10 +148,12 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kWarpP) {
+  if (warp >= kWarpP && warp < kWarpM) {
     // ================================ producer ================================
     uint32_t it = 0;
     int tn = 0;
+    const int pw = warp - kWarpP;
+    const bool lead = lane == 0 && pw == 0;  // issues the bulk copies
     // De-phase the two CTAs of an SM (and neighbouring SMs): all CTAs start together, so without a stagger the
     // whole chip gathers at once and then writes at once, saturating HBM in bursts and idling it in between.
     if (p.stagger_ns > 0) {
@@ -161,10 +166,10 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
       tile_rows(p, tile, row0, cnt);
       // source rows of this lane's 4 tile rows, for both gather index vectors: all index loads of the tile
       // are issued together, so no K-block waits on a dependent index load
-      int64_t src0[4], src1[4];
+      int64_t src0[RPW], src1[RPW];
 #pragma unroll
-      for (int rr = 0; rr < 4; ++rr) {
-        const int r = lane + 32 * rr;
+      for (int rr = 0; rr < RPW; ++rr) {
+        const int r = lane + 32 * (pw * RPW + rr);
         const bool ok = r < cnt;
         const int32_t* i0 = p.in_mode == IN_RAW ? p.raw_idx : (p.in_mode == IN_GATHER3 ? p.idx0 : nullptr);
         const int32_t* i1 = p.in_mode == IN_GATHER3 ? p.idx1 : nullptr;
@@ -176,14 +181,14 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
           if (l == 0) {
             // ---- A tile kb of the layer-0 operand
             const int s = it % kRing;
-            if (lane == 0) trace_ev(p.trace, 3, tn);  // P0: before slot wait (A tile)
+            if (lead) trace_ev(p.trace, 3, tn);  // P0: before slot wait (A tile)
             mbar_wait(empty_bar(s), ((it / kRing) & 1) ^ 1);
-            if (lane == 0) trace_ev(p.trace, 3, tn);  // P1: slot free
+            if (lead) trace_ev(p.trace, 3, tn);  // P1: slot free
             const uint32_t dst = s_ring + s * kTileB;
             if (p.in_mode == IN_RAW) {
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                const int r = lane + 32 * rr;
+              for (int rr = 0; rr < RPW; ++rr) {
+                const int r = lane + 32 * (pw * RPW + rr);
                 const bool ok = r < cnt;
                 const int64_t src_row = src0[rr];
 #pragma unroll 1
@@ -202,7 +207,7 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
               mbar_arrive(full_bar(s));
             } else if (p.in_mode == IN_GATHER3 && (kb >> 1) == 2 && p.x2_img != nullptr) {
               // the tile's own rows of the third segment are stored as a tile image: one bulk copy per K-block
-              if (lane == 0) {
+              if (lead) {
                 mbar_arrive_expect_tx(full_bar(s), (uint32_t)kTileB);
                 bulk_g2s(dst, reinterpret_cast<const uint8_t*>(p.x2_img) + (size_t)tile * 2 * kTileB + (size_t)(kb & 1) * kTileB,
                          (uint32_t)kTileB, full_bar(s));
@@ -220,8 +225,8 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
                 src_base = seg == 0 ? p.x0 : p.x1;
               }
 #pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                const int r = lane + 32 * rr;
+              for (int rr = 0; rr < RPW; ++rr) {
+                const int r = lane + 32 * (pw * RPW + rr);
                 const bool ok = r < cnt;
                 const int64_t src_row = ok ? (which == 0 ? src0[rr] : (which == 1 ? src1[rr] : row0 + r)) : 0;
                 const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + src_row * 128 + (kb & 1) * 64);
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(32 * (EW + 2), RING == kRingShared ? 2 : 1) ml
           // ---- weight tile (l, kb)
           const int s = it % kRing;
           mbar_wait(empty_bar(s), ((it / kRing) & 1) ^ 1);
-          if (lane == 0) {
+          if (lead) {
             const uint32_t bytes = (l == L - 1 && p.fin_mode == FIN_LINEAR) ? 16u * 128u : (uint32_t)kTileB;
             mbar_arrive_expect_tx(full_bar(s), bytes);
             bulk_g2s(s_ring + s * kTileB, reinterpret_cast<const uint8_t*>(p.wimg[l]) + (size_t)kb * kTileB, bytes,
@@ -569,9 +574,9 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
     auto set = [&](const void* f, uint32_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     };
-    set((const void*)mlp_fwd_kernel<4, kRingShared>, Lay<kRingShared>::kLaunch);
-    set((const void*)mlp_fwd_kernel<8, kRingShared>, Lay<kRingShared>::kLaunch);
-    set((const void*)mlp_fwd_kernel<8, kRingDeep>, Lay<kRingDeep>::kLaunch);
+    set((const void*)mlp_fwd_kernel<4, kRingShared, 1>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingShared, 1>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingDeep, 4>, Lay<kRingDeep>::kLaunch);
     if (e != cudaSuccess) return e;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -596,11 +601,11 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
     deep_ok = (e && atoi(e) == 0) ? 0 : 1;
   }
   if (fwd_epilogue_warps() == 4)
-    mlp_fwd_kernel<4, kRingShared><<<grid, 32 * 6, Lay<kRingShared>::kLaunch, st>>>(q);
+    mlp_fwd_kernel<4, kRingShared, 1><<<grid, 32 * 6, Lay<kRingShared>::kLaunch, st>>>(q);
   else if (deep_ok && p.n_tiles <= n_sm)
-    mlp_fwd_kernel<8, kRingDeep><<<grid, 32 * 10, Lay<kRingDeep>::kLaunch, st>>>(q);
+    mlp_fwd_kernel<8, kRingDeep, 4><<<grid, 32 * 13, Lay<kRingDeep>::kLaunch, st>>>(q);
   else
-    mlp_fwd_kernel<8, kRingShared><<<grid, 32 * 10, Lay<kRingShared>::kLaunch, st>>>(q);
+    mlp_fwd_kernel<8, kRingShared, 1><<<grid, 32 * 10, Lay<kRingShared>::kLaunch, st>>>(q);
   return cudaGetLastError();
 }
 
