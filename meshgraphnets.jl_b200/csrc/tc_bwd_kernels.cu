@@ -50,8 +50,8 @@ constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemH = kSmemZ + kZ * kImg;
 constexpr uint32_t kSmemW = kSmemH + kH * kImg;
 constexpr uint32_t kSmemScale = kSmemW + kW * kTileB;         // ln scale [128]
-constexpr uint32_t kSmemIdx = kSmemScale + 512;               // gather rows of the tile's dy_b, 128 ints
-constexpr uint32_t kSmemBar = kSmemIdx + 512;                 // (the head's final [8][3][128] reduction reuses a dZ slot)
+constexpr uint32_t kSmemIdx = kSmemScale + 512;               // gather rows of dy_b of this and of the next tile, 2 x 128 ints
+constexpr uint32_t kSmemBar = kSmemIdx + 1024;                // (the head's final [8][3][128] reduction reuses a dZ slot)
 constexpr uint32_t kNumBar = 2 * kZ + 2 * kH + 2 * kW + 4;
 constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
 constexpr uint32_t kSmemTotal = kSmemTmem + 16;
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     }
     if (tid == 0) bulk_wait0();
   } else {
-    // ================================ head: LayerNorm backward (16 lanes per row, 16 rows in flight per pass) =====
+    // ================================ head: LayerNorm backward (16 lanes per row, 2 x 32 rows in flight) =====
     const int lt = tid - 128, cc = lt & 15, rg = lt >> 4;  // rg in [0, 16)
     float gs[8], gb[8], dbt[8], sc[8];
 #pragma unroll
@@ -331,77 +331,84 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       for (int e = 0; e < 8; ++e) sc[e] = scale_s[cc * 8 + e];
       uint32_t t_local = 0;
       int tn = 0;
+      // gather rows of dy_b, one coalesced load per tile, fetched ONE TILE AHEAD into the other half of idx_s so that
+      // no batch ever waits on a dependent index load (the barrier that ends a tile publishes the next tile's rows)
+      auto fetch_idx = [&](int tile, uint32_t buf) {
+        if (p.dy_b && lt < kTile && tile < p.n_tiles) {
+          int64_t r0;
+          int n;
+          tile_rows(p.tile_row_start, p.M, tile, r0, n);
+          idx_s[buf * kTile + lt] = lt < n ? (p.b_idx ? p.b_idx[r0 + lt] : (int)(r0 + lt)) : 0;
+        }
+      };
+      fetch_idx(blockIdx.x, 0);
+      named_bar_sync(2, kHeadThreads);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         int64_t row0;
         int cnt;
         tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
         const uint32_t zs = t_local & 1;
+        const int* idx_c = idx_s + (t_local & 1) * kTile;
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L0: tile start
-        mbar_wait(z_empty(zs), ((t_local >> 1) & 1) ^ 1);
-        if (lt == 0) trace_ev(p.trace, 0, tn);  // L1: may write
         const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint32_t zb = z_slot(zs) + (cc >> 3) * kTileB;
-        // gather rows of dy_b for the whole tile: one coalesced load, so that the batches below never wait on
-        // a dependent index load (the previous tile's readers are past the barrier that ended their tile)
-        if (p.dy_b) {
-          if (lt < kTile) idx_s[lt] = lt < cnt ? (p.b_idx ? p.b_idx[row0 + lt] : (int)(row0 + lt)) : 0;
-          named_bar_sync(2, kHeadThreads);
-        }
-#pragma unroll 1
-        for (int b0 = 0; b0 < kTile; b0 += 64) {
-          // every load of 4 rows is issued before the first use (7 x 16 B per row and thread)
-          float4 a0[4], a1[4], c0[4], c1[4];
-          uint4 xq[4];
-          float rs[4];
+        // Four batches of 32 rows (2 per thread: i = 32 b + 2 rg + u), double buffered: the 14 loads of batch b + 1
+        // (7 x 16 B per row) are in flight while batch b is computed, so the memory pipe never drains between batches.
+        float4 a0[4], a1[4], c0[4], c1[4];  // [buffer h][row u] at 2 h + u
+        uint4 xq[4];
+        float rs[4];
+        auto issue = [&](int b, int h) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = b0 + rg * 4 + u;
-            a0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            a1[u] = a0[u];
-            c0[u] = a0[u];
-            c1[u] = a0[u];
-            xq[u] = make_uint4(0u, 0u, 0u, 0u);
-            rs[u] = 0.f;
+          for (int u = 0; u < 2; ++u) {
+            const int i = 32 * b + rg * 2 + u, k = 2 * h + u;
+            a0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            a1[k] = a0[k];
+            c0[k] = a0[k];
+            c1[k] = a0[k];
+            xq[k] = make_uint4(0u, 0u, 0u, 0u);
+            rs[k] = 0.f;
             if (i < cnt) {
               const int64_t r = row0 + i;
               if (p.dy_a) {
-                a0[u] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
-                a1[u] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
+                a0[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
+                a1[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
               }
               if (p.dy_b) {
                 // consecutive CSR rows share their receiver: reuse the previous row's gather instead of asking L2
-                // again (in-degree d => d-1 of d gathers saved; the max-carveout shared memory leaves no L1)
-                const int br = idx_s[i];
-                if (u > 0 && br == idx_s[i - 1]) {
-                  c0[u] = c0[u - 1];
-                  c1[u] = c1[u - 1];
+                // again (the max-carveout shared memory leaves no L1)
+                const int br = idx_c[i];
+                if (u > 0 && br == idx_c[i - 1]) {
+                  c0[k] = c0[k - 1];
+                  c1[k] = c1[k - 1];
                 } else {
-                  c0[u] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8);
-                  c1[u] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8 + 4);
+                  c0[k] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8);
+                  c1[k] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8 + 4);
                 }
               }
-              xq[u] = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
-              rs[u] = p.rstd[r];
+              xq[k] = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
+              rs[k] = p.rstd[r];
             }
           }
+        };
+        auto compute = [&](int b, int h) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = b0 + rg * 4 + u;
-            const float dy[8] = {a0[u].x + c0[u].x, a0[u].y + c0[u].y, a0[u].z + c0[u].z, a0[u].w + c0[u].w,
-                                 a1[u].x + c1[u].x, a1[u].y + c1[u].y, a1[u].z + c1[u].z, a1[u].w + c1[u].w};
-            const uint32_t xw[4] = {xq[u].x, xq[u].y, xq[u].z, xq[u].w};
+          for (int u = 0; u < 2; ++u) {
+            const int i = 32 * b + rg * 2 + u, k = 2 * h + u;
+            const float dy[8] = {a0[k].x + c0[k].x, a0[k].y + c0[k].y, a0[k].z + c0[k].z, a0[k].w + c0[k].w,
+                                 a1[k].x + c1[k].x, a1[k].y + c1[k].y, a1[k].z + c1[k].z, a1[k].w + c1[k].w};
+            const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
             float xh[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               xh[2 * e] = bf16_bits_to_float(xw[e] & 0xffffu);
               xh[2 * e + 1] = __uint_as_float(xw[e] & 0xffff0000u);
             }
-            float s1 = 0.f, s2 = 0.f;
+            float s1 = 0.f, s2 = 0.f, dxh[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float dxh = dy[e] * sc[e];
-              s1 += dxh;
-              s2 = fmaf(dxh, xh[e], s2);
+              dxh[e] = dy[e] * sc[e];
+              s1 += dxh[e];
+              s2 = fmaf(dxh[e], xh[e], s2);
               gb[e] += dy[e];
               gs[e] = fmaf(dy[e], xh[e], gs[e]);
             }
@@ -414,14 +421,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a = rs[u] * (dy[2 * e] * sc[2 * e] - m1 - xh[2 * e] * m2);
-              const float b = rs[u] * (dy[2 * e + 1] * sc[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
-              w[e] = pack_bf16x2(a, b);
+              const float a = rs[k] * (dxh[2 * e] - m1 - xh[2 * e] * m2);
+              const float b2 = rs[k] * (dxh[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
+              w[e] = pack_bf16x2(a, b2);
               dbt[2 * e] += bf16_bits_to_float(w[e] & 0xffffu);
               dbt[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
             }
             st_shared_v4(zb + t128_off(i, cc & 7), w[0], w[1], w[2], w[3]);
           }
+        };
+        issue(0, 0);  // the first batch is in flight while the dZ slot of this tile is still being read
+        fetch_idx(tile + gridDim.x, (t_local & 1) ^ 1);
+        mbar_wait(z_empty(zs), ((t_local >> 1) & 1) ^ 1);
+        if (lt == 0) trace_ev(p.trace, 0, tn);  // L1: may write
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b + 1 < 4) issue(b + 1, (b + 1) & 1);
+          compute(b, b & 1);
           if (lt == 0) trace_ev(p.trace, 0, tn);  // Lb: one batch of rows done
         }
         fence_proxy_async();
