@@ -498,7 +498,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 // Input kernel
 // ======================================================================================================
 namespace input {
-constexpr int kThreads = 192;  // warps 0-3 epilogue, 4 producer, 5 MMA
+constexpr int kNP = 2;                       // producer warps: each stages 64 of the 128 rows of a gathered block
+constexpr int kWarpP = 4, kWarpM = 4 + kNP;
+constexpr int kThreads = 32 * (kWarpM + 1);  // warps 0-3 epilogue, 4..4+kNP-1 producers, then the MMA warp
 constexpr int kZ = 2, kX = 2, kW = 3;
 constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemX = kSmemZ + kZ * kImg;
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
       mbar_init(z_empty(s), 1);
     }
     for (int s = 0; s < kX; ++s) {
-      mbar_init(x_full(s), 32);
+      mbar_init(x_full(s), 32 * kNP);
       mbar_init(x_empty(s), 1);
     }
     for (int s = 0; s < kW; ++s) {
@@ -553,21 +555,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 5) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp >= kWarpP && warp < kWarpM) {
     // ================================ producer ================================
     uint32_t xc = 0, wc = 0, t_local = 0;
     int tn = 0;
+    const int pw = warp - kWarpP;
+    const bool lead = lane == 0 && pw == 0;  // issues every bulk copy
+    constexpr int RPW = 4 / kNP;             // 32-row groups per producer warp
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
       int64_t row0;
       int cnt;
       tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
-      if (lane == 0) {
+      if (lead) {
         const uint32_t zs = t_local % kZ;
         mbar_wait(z_empty(zs), ((t_local / kZ) & 1) ^ 1);
         mbar_arrive_expect_tx(z_full(zs), kImg);
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
       }
       __syncwarp();
       for (int b = 0; b < nblk; ++b) {
-        if (lane == 0) {
+        if (lead) {
           for (int kb = 0; kb < 2; ++kb) {
             const uint32_t c = wc + kb, s = c % kW;
             mbar_wait(w_empty(s), ((c / kW) & 1) ^ 1);
@@ -587,32 +592,32 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         wc += 2;
         __syncwarp();
         const uint32_t xs = xc % kX;
-        if (lane == 0) trace_ev(p.trace, 3, tn);  // P0: before X slot wait
+        if (lead) trace_ev(p.trace, 3, tn);  // P0: before X slot wait
         mbar_wait(x_empty(xs), ((xc / kX) & 1) ^ 1);
-        if (lane == 0) trace_ev(p.trace, 3, tn);  // P1: slot free, gather starts
+        if (lead) trace_ev(p.trace, 3, tn);  // P1: slot free, gather starts
         const __nv_bfloat16* src_base = p.x[b];
         const int32_t* idx = p.idx[b];
         const uint32_t dst = x_slot(xs);
         if (p.x_is_img[b]) {  // the tile's own rows, stored as a tile image: one bulk copy
-          if (lane == 0) {
+          if (lead) {
             mbar_arrive_expect_tx(x_full(xs), kImg);
             bulk_g2s(dst, reinterpret_cast<const uint8_t*>(src_base) + (size_t)tile * kImg, kImg, x_full(xs));
           } else {
             mbar_arrive(x_full(xs));
           }
-          if (lane == 0) trace_ev(p.trace, 3, tn);  // P2: image copy issued
+          if (lead) trace_ev(p.trace, 3, tn);  // P2: image copy issued
           ++xc;
           continue;
         }
-        int64_t srow[4];
+        int64_t srow[RPW];
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {  // the 4 index loads of this lane are in flight together
-          const int r = lane + 32 * rr;
+        for (int rr = 0; rr < RPW; ++rr) {  // the index loads of this lane are in flight together
+          const int r = lane + 32 * (pw * RPW + rr);
           srow[rr] = r < cnt ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
         }
 #pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-          const int r = lane + 32 * rr;
+        for (int rr = 0; rr < RPW; ++rr) {
+          const int r = lane + 32 * (pw * RPW + rr);
           const bool ok = r < cnt;
           const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + srow[rr] * 128);
 #pragma unroll
@@ -620,11 +625,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
             cp_async16(dst + (c >> 3) * kTileB + t128_off(r, c & 7), src + c * 16, ok ? 16u : 0u);
         }
         cp_async_arrive_noinc(x_full(xs));
-        if (lane == 0) trace_ev(p.trace, 3, tn);  // P2: gather issued
+        if (lead) trace_ev(p.trace, 3, tn);  // P2: gather issued
         ++xc;
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kWarpM) {
     // ================================ MMA issue ================================
     if (lane == 0) {
       const uint32_t idesc_k = umma_idesc(128, 128, false, false);
@@ -638,6 +643,21 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         mbar_wait(z_full(zs), (t_local / kZ) & 1);
         trace_ev(p.trace, 1, tn);  // M1: dZ0 there
         tc_fence_after();
+        // dX of block b is issued BEFORE the weight-gradient MMAs of block b - 1: the epilogue gets its accumulator one
+        // gather latency earlier and the X block of b - 1 has the whole dX(b) time more to arrive.
+        auto issue_dw = [&](int b) {
+          const uint32_t xs = xc % kX;
+          mbar_wait(x_full(xs), (xc / kX) & 1);
+          trace_ev(p.trace, 1, tn);  // M3: X block there
+          fence_proxy_async();
+          tc_fence_after();
+          const uint32_t d_w = tmem + 128u * (1 + b);
+          for (int ks = 0; ks < 8; ++ks)
+            umma(d_w, desc_mnmajor(x_slot(xs), (uint32_t)kTileB, ks), desc_mnmajor(z_slot(zs), (uint32_t)kTileB, ks),
+                 idesc_mn, (t_local | ks) != 0);
+          umma_commit(x_empty(xs));
+          ++xc;
+        };
         for (int b = 0; b < nblk; ++b) {
           if (!first) {
             mbar_wait(acc_empty, acc_par);
@@ -655,18 +675,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           }
           umma_commit(acc_full);
           trace_ev(p.trace, 1, tn);  // M2: dX issued
-          const uint32_t xs = xc % kX;
-          mbar_wait(x_full(xs), (xc / kX) & 1);
-          trace_ev(p.trace, 1, tn);  // M3: X block there
-          fence_proxy_async();
-          tc_fence_after();
-          const uint32_t d_w = tmem + 128u * (1 + b);
-          for (int ks = 0; ks < 8; ++ks)
-            umma(d_w, desc_mnmajor(x_slot(xs), (uint32_t)kTileB, ks), desc_mnmajor(z_slot(zs), (uint32_t)kTileB, ks),
-                 idesc_mn, (t_local | ks) != 0);
-          umma_commit(x_empty(xs));
-          ++xc;
+          if (b > 0) issue_dw(b - 1);
         }
+        issue_dw(nblk - 1);
         umma_commit(z_empty(zs));
       }
       umma_commit(done_bar);
@@ -811,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 512);
+  if (warp == kWarpM) tmem_dealloc(tmem, 512);
 }
 }  // namespace input
 
