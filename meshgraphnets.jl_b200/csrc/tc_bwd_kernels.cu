@@ -498,9 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 // Input kernel
 // ======================================================================================================
 namespace input {
+constexpr int kEW = 8;                       // epilogue warps: two threads per tile row, each owns 64 accumulator columns
+constexpr int kEpi = 32 * kEW;
 constexpr int kNP = 2;                       // producer warps: each stages 64 of the 128 rows of a gathered block
-constexpr int kWarpP = 4, kWarpM = 4 + kNP;
-constexpr int kThreads = 32 * (kWarpM + 1);  // warps 0-3 epilogue, 4..4+kNP-1 producers, then the MMA warp
+constexpr int kWarpP = kEW, kWarpM = kEW + kNP;
+constexpr int kThreads = 32 * (kWarpM + 1);  // warps 0..kEW-1 epilogue, then kNP producers, then the MMA warp
 constexpr int kZ = 2, kX = 2, kW = 3;
 constexpr uint32_t kSmemZ = 0;
 constexpr uint32_t kSmemX = kSmemZ + kZ * kImg;
@@ -551,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
       mbar_init(w_empty(s), 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, kEpi);
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
@@ -684,8 +686,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     }
   } else {
     // ================================ epilogue ================================
-    const int row = tid;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int row = tid & 127, half = tid >> 7;
+    const int c_lo = 2 * half, c_hi = c_lo + 2;  // 32-column accumulator chunks of this thread
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t acc_par = 0;
     int tn = 0;
     bool stage_store_pending = false;
@@ -696,16 +699,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
 #pragma unroll 1
       for (int b = 0; b < nblk; ++b) {
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: block start
-        // SINK_ADD_F32 with a source: the tile's fp32 rows (16 per thread) are requested NOW, before the wait for the
+        // SINK_ADD_F32 with a source: the tile's fp32 rows (8 per thread) are requested NOW, before the wait for the
         // accumulator and the staging pass, so that their latency is off the critical path (1 CTA/SM: registers abound)
-        float4 pr0[16], pr1[16];
+        float4 pr0[8], pr1[8];
         const bool prefetch = p.sink[b] == SINK_ADD_F32 && p.f32_src[b] != nullptr;
         if (prefetch) {
           const int pcc = tid & 15, prg = tid >> 4;
           const float* src = p.f32_src[b];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int i = prg + 8 * u;
+          for (int u = 0; u < 8; ++u) {
+            const int i = prg + 16 * u;
             pr0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             pr1[u] = pr0[u];
             if (i < cnt) {
@@ -723,14 +726,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           bulk_wait_read0();
           stage_store_pending = false;
         }
-        named_bar_sync(1, 128);  // the previous copy-out has finished reading the staging tile
+        named_bar_sync(1, kEpi);  // the previous copy-out has finished reading the staging tile
         if (p.sink[b] == SINK_SEGSUM_F32) {  // tile-local CSR row pointer (visible after the next barrier)
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
           if (tid <= nn) rp_s[tid] = p.row_ptr[n0 + tid] - (int)row0;
           if (tid == 0 && nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
         }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = c_lo; c < c_hi; ++c) {
           float v[32];
           tmem_ld32(t_lane + c * 32, v);
           const uint32_t sb = s_stage + (c >> 1) * kTileB;
@@ -743,7 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         tc_fence_before();
         mbar_arrive(acc_empty);
         if (p.sink[b] == SINK_STORE_IMG) fence_proxy_async();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpi);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: staged
         const int sink = p.sink[b];
         if (sink == SINK_STORE_IMG) {
@@ -756,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         } else if (sink == SINK_STORE_BF16) {
           const int cc = tid & 15, rg = tid >> 4;
 #pragma unroll 4
-          for (int i = rg; i < cnt; i += 8) {
+          for (int i = rg; i < cnt; i += kEpi / 16) {
             const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
             *reinterpret_cast<uint4*>(p.bf16_dst[b] + (row0 + i) * 128 + cc * 8) = q;
           }
@@ -764,8 +767,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           // dst = src + dX; the source rows were prefetched at the top of the block
           const int cc = tid & 15, rg = tid >> 4;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int i = rg + 8 * u;
+          for (int u = 0; u < 8; ++u) {
+            const int i = rg + 16 * u;
             if (i >= cnt) continue;
             const uint4 q = ld_shared_v4(s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7));
             const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
@@ -791,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
           const bool in_place = p.f32_src[b] != nullptr;
           float* dst = p.f32_dst[b] + (int64_t)n0 * 128;
-          segsum_tile<false>(s_stage, s_base + kSmemRp, nn, tid, nullptr, nullptr,
+          segsum_tile<false, 4>(s_stage, s_base + kSmemRp, nn, tid, nullptr, nullptr,
                              [&](int v, int col0, const float (&a)[8]) {
                                float* d = dst + (int64_t)v * 128 + col0;
                                if (in_place) {
@@ -811,7 +814,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     tc_fence_after();
     for (int b = 0; b < nblk; ++b) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = c_lo; c < c_hi; ++c) {
         float v[32];
         tmem_ld32(t_lane + 128u * (1 + b) + c * 32, v);
         float4* dst = reinterpret_cast<float4*>(my_partial + (size_t)b * 16384 + (size_t)row * 128 + c * 32);
