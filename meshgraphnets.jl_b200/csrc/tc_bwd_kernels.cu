@@ -860,6 +860,47 @@ __global__ void __launch_bounds__(256) reduce_pieces_kernel(const Pieces pieces,
   }
 }
 
+// The same sum, four outputs per thread (128-bit loads): used when every piece is 16-byte aligned with counts and
+// strides that are multiples of 4 - all pieces but the decoder's last layer.  Per output the parts are added in exactly
+// the order of the scalar kernel (parts y, y+8, ... then the 8 groups), so both kernels give the same bits.
+__global__ void __launch_bounds__(256) reduce_pieces4_kernel(const Pieces pieces, int64_t total4) {
+  __shared__ float4 red[8][33];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + x;
+  int64_t e = i < total4 ? i : total4 - 1;
+  int k = 0;
+  while (k < pieces.n - 1 && e >= (pieces.p[k].count >> 2)) {
+    e -= pieces.p[k].count >> 2;
+    ++k;
+  }
+  const float4* src = reinterpret_cast<const float4*>(pieces.p[k].src) + e;
+  const int64_t stride4 = pieces.p[k].stride >> 2;
+  const int n_parts = pieces.p[k].n_parts;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int q = y; q < n_parts; q += 8) {
+    const float4 v = src[(int64_t)q * stride4];
+    s.x += v.x;
+    s.y += v.y;
+    s.z += v.z;
+    s.w += v.w;
+  }
+  red[y][x] = s;
+  __syncthreads();
+  if (y == 0 && i < total4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 v = red[g][x];
+      t.x += v.x;
+      t.y += v.y;
+      t.z += v.z;
+      t.w += v.w;
+    }
+    reinterpret_cast<float4*>(pieces.p[k].dst)[e] = t;
+  }
+}
+
 // Address of element (row, col) of a [tile][2][16 KB] image, in bytes from the tile base.
 __device__ __forceinline__ uint32_t img_off(int row, int col) {
   return (uint32_t)(col >> 6) * (uint32_t)kTileB + t128_off(row, (col & 63) >> 3) + (uint32_t)(col & 7) * 2u;
@@ -1077,8 +1118,15 @@ cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st) {
   int64_t total = 0;
   for (int i = 0; i < pieces.n; ++i) total += pieces.p[i].count;
   if (total == 0) return cudaSuccess;
+  bool vec = true;
+  for (int i = 0; i < pieces.n; ++i) {
+    const Piece& q = pieces.p[i];
+    vec = vec && (q.count & 3) == 0 && (q.stride & 3) == 0 && (reinterpret_cast<uintptr_t>(q.src) & 15) == 0 &&
+          (reinterpret_cast<uintptr_t>(q.dst) & 15) == 0;
+  }
   ProfScope ps(TAG_REDUCE_PARTIALS, st);
-  reduce_pieces_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(pieces, total);
+  if (vec) reduce_pieces4_kernel<<<(unsigned)((total / 4 + 31) / 32), 256, 0, st>>>(pieces, total / 4);
+  else reduce_pieces_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(pieces, total);
   return cudaGetLastError();
 }
 
