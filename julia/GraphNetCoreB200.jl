@@ -153,4 +153,58 @@ shooting_continuity!(loss, da, a, b, w) = (check(ccall((:mgn_shooting_continuity
     (CuPtr{Float32}, CuPtr{Float32}, Int64, Float32, CuPtr{Float32}, CuPtr{Float32}, Ptr{Cvoid}),
     a, b, length(a), Float32(w), loss, da, stream())); loss)
 
+# ---- lock-step MultipleShooting step (transcription of meshgraphnets.jl_b200/shooting.py; UNTESTED like the rest) ----
+# All K shooting intervals advance together as ONE block-diagonal graph (K copies of the mesh), fixed-step explicit
+# Euler (the examples/cylinder_flow configuration; the Python file also carries RK4 / Tsit5 tableaus), exact reverse
+# sweep through `backward` (d_params and d_nf).  Normaliser statistics are frozen during the step.
+#   rhs_forward(X, idx; training)  -> dX/dt for the stacked state X (S x K*N), idx[k] = data index of interval k's inflow
+#   rhs_backward(dY)               -> (d_params, dX) of the matching training forward
+# are closures the caller builds from build_graph / inverse_data exactly as ode_step does (src/solve.jl:188-219), with
+# the inflow overwrite (masked_overwrite!) in front and `.* val_mask` (vec_mul!) behind, over the K-fold repeated
+# senders / receivers (copy k shifted by k*N) - see DeviceRhs in shooting.py.
+function multiple_shooting_step(rhs_forward, rhs_backward, ps::CuVector{Float32}, gt::CuArray{Float32,3},
+        val_mask::CuMatrix{Float32}, tsteps::AbstractVector{Float32}, dt::Float32, interval_size::Int,
+        continuity_term)
+    S, N, _ = size(gt)
+    ranges = [i:min(length(tsteps), i + interval_size - 1) for i in 1:(interval_size - 1):(length(tsteps) - 1)]  # strategies.jl:346-347
+    K, M = length(ranges), maximum(length.(ranges)) - 1
+    firsts = first.(ranges)
+    idx_of(t) = min(floor(Int, t / dt) + 1, size(gt, 3))                       # src/solve.jl:106
+    X = reduce(hcat, [gt[:, :, f] for f in firsts])                            # S x K*N, u0 of every interval
+    saves, chk = [X], Tuple{typeof(X),Vector{Int}}[]
+    for m in 0:(M - 1)                                                         # forward sweep, states checkpointed
+        idx = [idx_of(tsteps[min(f + m, length(tsteps))]) for f in firsts]
+        push!(chk, (X, idx))
+        k1 = rhs_forward(X, idx; training = false)
+        X = ode_lincomb!(similar(X), X, [k1], [dt])
+        push!(saves, X)
+    end
+    loss = CUDA.zeros(Float32, 1)
+    dsaves = [CUDA.zeros(Float32, S, K * N) for _ in 0:M]
+    for (k, rg) in enumerate(ranges)                                           # strategies.jl:367-383
+        cols = ((k - 1) * N + 1):(k * N)
+        P = cat([saves[m][:, cols] for m in 1:length(rg)]...; dims = 3)
+        dP = similar(P)
+        shooting_mse!(loss, dP, P, gt[:, :, rg], val_mask; accumulate = true)
+        if k < K                                                               # continuity term of interval k + 1
+            last = dP[:, :, end]
+            shooting_continuity!(loss, last, P[:, :, end], gt[:, :, first(ranges[k + 1])], continuity_term)
+            dP[:, :, end] .= last
+        end
+        for m in 1:length(rg)
+            dsaves[m][:, cols] .= dP[:, :, m]
+        end
+    end
+    g, lam = CUDA.zeros(Float32, length(ps)), copy(dsaves[end])
+    for n in M:-1:1                                                            # reverse sweep (Euler: one stage)
+        x, idx = chk[n]
+        rhs_forward(x, idx; training = true)
+        gi, dx = rhs_backward(ode_lincomb!(similar(lam), CUDA.zeros(Float32, size(lam)), [lam], [dt]))
+        ode_lincomb!(g, g, [gi], [1.0f0])
+        ode_lincomb!(lam, lam, [dx], [1.0f0])
+        n > 1 && ode_lincomb!(lam, lam, [dsaves[n]], [1.0f0])
+    end
+    (g,), loss
+end
+
 end # module
