@@ -153,3 +153,27 @@ def test_strategy_constructors_and_errors(shooting):
     with pytest.raises(ValueError):                                      # more time points than data
         cfg, p, make, _, N = _problem(seed=2, T=4)
         _run(shooting, make, p, N, tstart=0.0, dt=0.01, tstop=0.07, interval_size=4)
+
+
+def test_product_time_grid_and_interval_helpers_known_answers(shooting):
+    """The product's own restatement of `tstart:dt:tstop`, the interval ranges (src/strategies.jl:344-347) and the
+    inflow data index (src/solve.jl:106) against hand-derived values and against the oracle's."""
+    ts = shooting.time_steps(0.0, 0.01, 0.49)
+    assert ts.dtype == np.float32 and ts.shape == (50,) and ts[-1] == np.float32(0.49) and ts[7] == np.float32(0.07)
+    assert np.array_equal(ts, sol.tsteps(0.0, 0.01, 0.49))
+    assert shooting.time_steps(0.5, 0.25, 1.3).tolist() == [0.5, 0.75, 1.0, 1.25]          # stop not on the grid
+    with pytest.raises(ValueError):
+        shooting.time_steps(0.0, 0.0, 1.0)
+    assert shooting.shooting_ranges(11, 4) == [(0, 3), (3, 6), (6, 9), (9, 10)] == sol.shooting_ranges(11, 4)
+    assert shooting.shooting_ranges(50, 6) == sol.shooting_ranges(50, 6) and len(shooting.shooting_ranges(50, 6)) == 10
+    with pytest.raises(ValueError):
+        shooting.shooting_ranges(11, 1)
+    for n in (0, 1, 7, 40):
+        for world in (1, 2, 3, 8):
+            parts = [shooting.shard_intervals(n, r, world) for r in range(world)]
+            assert sorted(sum(parts, [])) == list(range(n)) and max(map(len, parts)) - min(map(len, parts)) <= 1
+    # floor(Int, t / dt) + 1 in Float32, 0-based here, clamped to the data
+    from meshgraphnets_jl_b200.shooting import inflow_index
+    assert [inflow_index(np.float32(0.01) * k, 0.01, 100) for k in range(5)] == [0, 1, 2, 3, 4]
+    assert inflow_index(np.float32(0.0198), 0.01, 100) == 1 and inflow_index(np.float32(0.07), 0.01, 5) == 4
+    assert all(inflow_index(t, 0.01, 100) == orc.inflow_index(t, 0.01) for t in np.linspace(0, 0.9, 181, dtype=np.float32))
