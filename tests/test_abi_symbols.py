@@ -93,3 +93,26 @@ def test_device_entry_points_fail_without_a_gpu(pkg):
     h = C.c_void_p()
     st = lib.mgn_model_create(C.byref(ModelConfig(9, 3, 2, 128, 2, 2, 1e-5, 1)), C.byref(h))
     assert st == 2     # the bf16 model uploads its weight-image plan to the device: MGN_ERR_CUDA
+
+
+def test_plain_c_consumer_runs_the_known_answer_tests(tmp_path):
+    """tests/c/abi_kat.c is compiled as C11 against include/mgn_b200.h (the header must be C, not C++), linked with
+    libmgn_b200.so and run: the SURVEY 8c known-answer tests through the host half of the ABI, the parameter table of
+    the reference configuration, and - on a machine without a GPU - MGN_ERR_CUDA from the device entry points (no CPU
+    fallback)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "meshgraphnets.jl_b200", "csrc")
+    if not os.path.exists(os.path.join(libdir, "libmgn_b200.so")):
+        import __graft_entry__
+        __graft_entry__.build()
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    exe = str(tmp_path / "abi_kat")
+    r = subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                        os.path.join(root, "tests", "c", "abi_kat.c"), "-o", exe, "-L", libdir, "-lmgn_b200",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
