@@ -99,10 +99,52 @@ def sharded(mode):
         dist.destroy_process_group()
 
 
+def chain(mode):
+    """BASELINE configs[3]: 1-D chain of 100 000 nodes (src/dataset.jl:379-382 through parse_edges, E = 199 998,
+    F_e = 2), one target field `u` and one non-target input field, 15 MP steps, MultipleShooting with 26 observations
+    and interval_size 6 -> 5 intervals in lock-step = one 500 000-node / 999 990-edge block-diagonal graph, Euler."""
+    dev = torch.device("cuda", 0)
+    n, T = 100_000, 26
+    rng = np.random.default_rng(11)
+    pos = np.linspace(0.0, 1.0, n, dtype=np.float32)[:, None]
+    nt = np.zeros(n, dtype=np.int32)
+    nt[0], nt[-1] = 4, 5
+    xs = pos[:, 0]
+    u = np.stack([np.sin(2 * np.pi * (xs - 0.02 * k)) + 0.05 * rng.normal(size=n) for k in range(T)])[:, :, None]
+    load = np.cos(4 * np.pi * xs)[None, :, None].repeat(T, 0)
+    data_h = {"node_type": nt.reshape(1, -1, 1), "mesh_pos": pos[None], "edges": pkg.chain_edges(n)}
+    meta = {"dt": 0.01, "features": {"u": {"dim": 1}, "load": {"dim": 1}}, "target_features": ["u"]}
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0, device=dev)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    data = {"u": to(u.astype(np.float32)), "load": to(load.astype(np.float32)),
+            "node_type": to(nt.reshape(1, -1, 1).astype(np.int32))}
+    vm = to(pkg.val_mask(nt, [0], 1))
+    model, ps, st = pkg.build_model(1 + 1 + 7, 1, 1, 15, 128, 2, device=dev, compute_mode=mode, seed=5)
+    mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOfflineMeanStd(0.0, 1e-5),
+                           {"u": pkg.NormaliserOfflineMeanStd(0.0, 0.7), "load": pkg.NormaliserOfflineMinMax(-1.0, 1.0),
+                            "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
+                           {"u": pkg.NormaliserOfflineMeanStd(0.0, 3.0)})
+    strat = pkg.MultipleShooting(0.0, 0.01, 0.25, "euler", interval_size=6, continuity_term=100)
+    t = (mgn, data, meta, ["u", "load"], ["u"], node_type, ef, senders, receivers, 1, None, vm)
+    tt = pkg.init_train_step(strat, t, None)
+    n_int = len(pkg.shooting_ranges(T, 6))
+    ms, ((gs,), loss) = timed(lambda: pkg.train_step(strat, tt), 2)
+    E = int(senders.shape[0])
+    print(json.dumps({"workload": "chain_100k_multiple_shooting_step", "nodes": n, "edges": E, "mps": 15,
+                      "mode": "bf16" if mode == pkg.COMPUTE_BF16 else "fp32", "solver": "euler", "observations": T,
+                      "intervals": n_int, "lockstep_graph_nodes": n * n_int, "lockstep_graph_edges": E * n_int,
+                      "ms_per_train_step": ms,
+                      "mp_step_edges_per_sec_train_equiv": (5 + 5 / 3) * n_int * E * 15 / (ms * 1e-3),
+                      "loss": float(loss.cpu()), "grad_finite": bool(torch.isfinite(gs).all()),
+                      "hbm_gb_allocated": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+
+
 def main():
     mode = pkg.COMPUTE_BF16 if (len(sys.argv) < 2 or sys.argv[1] == "bf16") else pkg.COMPUTE_FP32
     if "--sharded" in sys.argv:
         return sharded(mode)
+    if "--chain" in sys.argv:
+        return chain(mode)
     dev = torch.device("cuda", 0)
     pos, cells, nt = pkg.cylinder_flow_mesh(65, 29)
     T = 50
