@@ -8,9 +8,9 @@ against the measured peaks of MEASURED_PEAKS.json.  The algorithmic work per uni
 layout of DESIGN.md section 3 (training mode, fp32 master latents + bf16 shadows):
 
   kernel family   FLOP / edge row          FLOP / node row        bytes / edge row   bytes / node row
-  forward         2 D^2 (L+2)              2 D^2 (L+1)            2572               3076 (+512: gather source + agg)
-  bwd chain       4 D^2 (L-1)              4 D^2 (L-1)            1540 + 512(d_agg)  1540
-  bwd input       12 D^2                   8 D^2                  2056               2816
+  forward         2 D^2 (L+2)              2 D^2 (L+1)            2572               2820 (+512: gather source + agg)
+  bwd chain       4 D^2 (L-1)              4 D^2 (L-1)            1796 (+512 d_agg per node)  1796
+  bwd input       12 D^2                   8 D^2                  1800               3840
 (bytes: every tensor the kernel must read or write once per row; gathered node rows are counted
 once per node, not once per edge - they are L2 hits after the first touch.)
 """
