@@ -120,7 +120,7 @@ stream() = CUDA.stream().handle
 
 # y = x + sum_j coef[j] * k[j]   (n_terms <= 8)
 function ode_lincomb!(y::CuArray{Float32}, x::CuArray{Float32}, ks::Vector{<:CuArray{Float32}}, coef::Vector{Float32})
-    ptrs = [reinterpret(Ptr{Cvoid}, pointer(k)) for k in ks]
+    ptrs = [Ptr{Cvoid}(UInt(pointer(k))) for k in ks]      # device addresses, passed by value in a HOST array
     GC.@preserve ks check(ccall((:mgn_ode_lincomb, LIB), Int32,
         (CuPtr{Float32}, Ptr{Ptr{Cvoid}}, Ptr{Float32}, Int32, Int64, CuPtr{Float32}, Ptr{Cvoid}),
         x, ptrs, coef, length(ks), length(y), y, stream()))
