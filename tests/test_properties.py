@@ -135,3 +135,36 @@ def test_pullback_is_linear_in_the_cotangent(seed, a, b):
     scale = max(np.abs(g1).max(), np.abs(g2).max(), 1e-30)
     assert np.allclose(g, a * g1 + b * g2, rtol=1e-9, atol=1e-11 * scale)
     assert np.allclose(x, a * x1 + b * x2, rtol=1e-9, atol=1e-11 * max(np.abs(x1).max(), np.abs(x2).max(), 1e-30))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 40), st.integers(0, 150), st.integers(1, 9), st.integers(0, 2 ** 31 - 1))
+def test_partition_plan_invariants_on_random_multigraphs(pkg, n_nodes, n_edges, world, seed):
+    """The halo-exchange plan (meshgraphnets.jl_b200/partition.py, integer work): random multigraphs with self loops,
+    repeated edges, isolated nodes and more ranks than nodes.  Every edge has exactly one owner (the owner of its
+    receiver), local ids map back to the global graph, halo rows are exactly the remote senders, the send / receive
+    lists of every pair of ranks describe the same rows in the same order, and the one-rank builder agrees."""
+    rng = np.random.default_rng(seed)
+    s = rng.integers(1, n_nodes + 1, size=n_edges).astype(np.int32)
+    r = rng.integers(1, n_nodes + 1, size=n_edges).astype(np.int32)
+    parts = pkg.build_partition(n_nodes, s, r, world)
+    assert [p.lo for p in parts] + [parts[-1].hi] == pkg.partition_bounds(n_nodes, world)
+    all_e = np.concatenate([p.edge_ids for p in parts]) if parts else np.zeros(0, np.int64)
+    assert np.array_equal(np.sort(all_e), np.arange(n_edges))
+    for p in parts:
+        glob = p.local_nodes_global()
+        assert np.array_equal(glob[p.senders - 1], s[p.edge_ids] - 1)
+        assert np.array_equal(glob[p.receivers - 1], r[p.edge_ids] - 1)
+        assert ((p.receivers - 1) < p.n_own).all() and (np.diff(p.edge_ids) > 0).all()
+        remote = np.unique(s[p.edge_ids][(s[p.edge_ids] - 1 < p.lo) | (s[p.edge_ids] - 1 >= p.hi)] - 1)
+        assert np.array_equal(p.halo_global, remote)
+        for q, rows in p.recv_rows.items():
+            assert np.array_equal(parts[q].send_rows[p.rank] + parts[q].lo, p.halo_global[rows - p.n_own])
+        covered = np.sort(np.concatenate(list(p.recv_rows.values()))) if p.recv_rows else np.zeros(0, np.int64)
+        assert np.array_equal(covered, np.arange(p.n_own, p.n_local))
+        one = pkg.build_partition_rank(n_nodes, s, r, world, p.rank)
+        assert np.array_equal(one.senders, p.senders) and np.array_equal(one.receivers, p.receivers)
+        assert np.array_equal(one.halo_global, p.halo_global) and np.array_equal(one.edge_ids, p.edge_ids)
+        assert set(one.send_rows) == set(p.send_rows) and set(one.recv_rows) == set(p.recv_rows)
+        assert all(np.array_equal(one.send_rows[q], p.send_rows[q]) for q in p.send_rows)
+        assert all(np.array_equal(one.recv_rows[q], p.recv_rows[q]) for q in p.recv_rows)
