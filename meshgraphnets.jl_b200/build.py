@@ -13,7 +13,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libmgn_b200.so")
-SOURCES = ["abi.cu", "csr.cu", "simt_kernels.cu", "solver_kernels.cu", "pipeline.cu", "tc_probe.cu", "tc_kernels.cu", "tc_bwd_kernels.cu", "tc_pipeline.cu"]
+SOURCES = ["abi.cu", "device_state.cu", "csr.cu", "simt_kernels.cu", "solver_kernels.cu", "pipeline.cu", "tc_kernels.cu",
+           "tc_bwd_kernels.cu", "tc_pipeline.cu"]
+# test-only probe of the tcgen05 building blocks: its own library, never linked into the product
+PROBE_LIB = os.path.join(CSRC, "libmgn_b200_probe.so")
+PROBE_SOURCES = ["tc_probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -31,15 +35,15 @@ def _digest(paths):
     return h.hexdigest()
 
 
-def _compile(src, verbose):
+def _compile(src, verbose, extra=()):
     obj = os.path.join(OBJ, src.replace(".cu", ".o"))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "mgn_b200.h"))
     stamp = obj + ".sha"
-    dig = _digest([os.path.join(CSRC, src)] + headers)
+    dig = _digest([os.path.join(CSRC, src)] + headers) + " ".join(extra)
     if os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, False
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -50,23 +54,33 @@ def _compile(src, verbose):
     return obj, True
 
 
-def build(verbose=False, force=False):
+def _link(lib, objs):
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+           "-Xcompiler", "-fPIC", "-o", lib] + objs + ["-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+
+
+def build(verbose=False, force=False, trace=False):
+    """Compiles every CUDA source for sm_100a and links libmgn_b200.so (+ the test-only probe library).
+    ``trace=True`` is the debug build with the per-role timestamp hooks (tools/trace_kernels.py)."""
     os.makedirs(OBJ, exist_ok=True)
-    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    srcs = [s for s in SOURCES + PROBE_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
+    extra = ("-DMGN_ENABLE_TRACE",) if trace else ()
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda s: _compile(s, verbose), srcs))
-    objs = [o for o, _ in results]
-    if any(changed for _, changed in results) or not os.path.exists(LIB):
-        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-Xcompiler", "-fPIC", "-o", LIB] + objs
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        results = dict(zip(srcs, ex.map(lambda s: _compile(s, verbose, extra), srcs)))
+    main = [results[s] for s in SOURCES if s in results]
+    if any(changed for _, changed in main) or not os.path.exists(LIB):
+        _link(LIB, [o for o, _ in main])
+    probe = [results[s] for s in PROBE_SOURCES if s in results]
+    if probe and (any(changed for _, changed in probe) or not os.path.exists(PROBE_LIB)):
+        _link(PROBE_LIB, [o for o, _ in probe])
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, trace="--trace" in sys.argv))

@@ -2,6 +2,7 @@
 // one replaces) and the host-side integer graph indexing that must match the reference
 // bit-exactly (one_hot, triangles_to_edges, parse_edges, the 0->1 based shift).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -27,8 +28,11 @@ static const char* kTagNames[TAG_COUNT] = {
     "tc_dw", "tc_misc", "solver"};
 const char* tag_name(int tag) { return tag >= 0 && tag < TAG_COUNT ? kTagNames[tag] : "?"; }
 
+// Diagnostic only (bench.py's launch count / per-family timing): off by default, and when off the launch path reads
+// one relaxed atomic and nothing else.  While a session is on, every access is serialised by `mu`.
 struct Profiler {
-  bool on = false;
+  std::atomic<bool> on{false};
+  std::mutex mu;
   int tag = -1;
   int64_t launches = 0;
   int64_t per_tag[TAG_COUNT] = {};
@@ -38,7 +42,8 @@ struct Profiler {
 static Profiler g_prof;
 
 ProfScope::ProfScope(int tag, cudaStream_t s) : st(s), slot(-1) {
-  if (!g_prof.on) return;
+  if (!g_prof.on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   ++g_prof.launches;
   if (tag >= 0 && tag < TAG_COUNT) ++g_prof.per_tag[tag];
   if (tag != g_prof.tag) return;
@@ -55,7 +60,9 @@ ProfScope::ProfScope(int tag, cudaStream_t s) : st(s), slot(-1) {
   g_prof.events.push_back(ev);
 }
 ProfScope::~ProfScope() {
-  if (slot >= 0) cudaEventRecord(g_prof.events[slot].second, st);
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  if (slot < (int)g_prof.events.size()) cudaEventRecord(g_prof.events[slot].second, st);
 }
 
 static void add_mlp(mgn_model* m, const std::string& name, int in_dim, int out_dim, bool ln,
@@ -286,6 +293,7 @@ int32_t mgn_model_create(const mgn_model_config* cfg, mgn_model** out) {
     MGN_REQUIRE(cfg->latent == 128, "model_create: MGN_COMPUTE_BF16 needs latent == 128");
   mgn_model* m = new mgn_model();
   m->cfg = *cfg;
+  m->knobs = read_tune_knobs();  // the only place the environment is read
   int64_t off = 0;
   const int D = cfg->latent;
   add_mlp(m, "encoder.node", cfg->node_in, D, true, off);
@@ -442,12 +450,13 @@ int32_t mgn_adam_step_device(float* d_params, const float* d_grads, float* d_m, 
 
 int32_t mgn_profile_begin(int32_t tag) {
   MGN_REQUIRE(tag >= -1 && tag < TAG_COUNT, "profile_begin: unknown tag");
-  g_prof.on = true;
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   g_prof.tag = tag;
   g_prof.launches = 0;
   for (auto& c : g_prof.per_tag) c = 0;
   for (auto& e : g_prof.events) g_prof.pool.push_back(e);
   g_prof.events.clear();
+  g_prof.on = true;
   return MGN_OK;
 }
 
@@ -455,6 +464,7 @@ int32_t mgn_profile_end(int64_t* n_launches, int64_t* n_tagged, float* tagged_ms
                         int32_t per_tag_capacity) {
   g_prof.on = false;
   MGN_CUDA_TRY(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_prof.mu);
   float total = 0.f;
   for (auto& e : g_prof.events) {
     float ms = 0.f;

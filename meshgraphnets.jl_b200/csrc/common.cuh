@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -31,6 +32,46 @@ int32_t fail(int32_t code, const std::string& msg);
     int32_t _s = (expr);               \
     if (_s != MGN_OK) return _s;       \
   } while (0)
+
+// ---- per-device library state (device_state.cu) -----------------------------------------------------
+// The library keeps NO process-global mutable state on the launch path: what has to be set up once per
+// CUDA device (opt-in shared-memory limits of the big kernels, the SM count) is guarded by one
+// std::call_once per device, so a process that switches devices (CUDA.device!, src/MeshGraphNets.jl:257)
+// or calls from several host threads launches correctly configured kernels on every device.
+constexpr int kMaxDevices = 64;
+class PerDeviceOnce {
+ public:
+  // Runs f(device) the first time it is called on the current device; every call returns f's status.
+  template <class F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::call_once(flag_[dev], [&] { err_[dev] = f(dev); });
+    return err_[dev];
+  }
+
+ private:
+  std::once_flag flag_[kMaxDevices];
+  cudaError_t err_[kMaxDevices] = {};
+};
+int device_sm_count();  // SMs of the current device (cached per device, thread-safe)
+// Scratch private to (current device, stream, kind): two calls on different streams or host threads never share
+// partial sums.  Allocated on first use under a mutex; if that first use happens inside a stream capture the
+// allocation is made with the thread's capture mode relaxed, so the capture stays valid.  A captured graph keeps
+// the scratch of its capture stream: replay one graph instance at a time.
+enum ScratchKind : int { SCRATCH_LOSS = 0, SCRATCH_NORM = 1, SCRATCH_KINDS };
+cudaError_t stream_scratch(cudaStream_t st, int kind, size_t bytes, void** out);
+void release_device_state();  // frees every scratch buffer (mgn_library_release)
+
+// Tuning knobs, read from the environment ONCE per model handle (mgn_model_create), never on the launch path.
+struct TuneKnobs {
+  int fwd_epi_warps = 8;   // MGN_FWD_EPI_WARPS=4 selects the one-thread-per-row epilogue
+  int fwd_stagger_ns = 0;  // MGN_FWD_STAGGER_NS
+  int fwd_deep_ring = 1;   // MGN_FWD_DEEP_RING=0 disables the deep-ring variant for small graphs
+};
+TuneKnobs read_tune_knobs();
 
 constexpr int kMaxDense = 8;
 constexpr int kOdeMaxTerms = 8;  // terms of one explicit Runge-Kutta combination (mgn_ode_lincomb)
@@ -66,6 +107,7 @@ namespace mgn { namespace tc { struct ModelImages; } }
 struct mgn_model {
   mgn_model_config cfg;
   mgn::tc::ModelImages* images = nullptr;  // packed-weight image plan (MGN_COMPUTE_BF16)
+  mgn::TuneKnobs knobs;                    // environment knobs, frozen at creation
   std::vector<mgn::MlpLayout> mlps;  // encoder.node, encoder.edge, (edge, node) x mps, decoder
   int64_t n_params = 0;
   int n_dense() const { return cfg.hidden_layers + 2; }

@@ -844,21 +844,16 @@ cudaError_t adam_step_device(float* p, const float* g, float* m, float* v, int64
 cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
                                cudaStream_t st) {
   if (F > kNormMaxF) return cudaErrorInvalidValue;
-  // per-device scratch for the block partials, allocated on first use (outside any stream capture: callers warm up
-  // before capturing).  One normaliser update at a time per device - the reference is single-stream.
-  static float* scratch[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!scratch[dev]) {
-    cudaError_t e = cudaMalloc(&scratch[dev], sizeof(float) * kNormBlocks * 2 * kNormMaxF);
-    if (e != cudaSuccess) return e;
-  }
+  // scratch for the block partials: private to (device, stream), see stream_scratch()
+  float* scratch = nullptr;
+  cudaError_t se = stream_scratch(st, SCRATCH_NORM, sizeof(float) * kNormBlocks * 2 * kNormMaxF,
+                                  reinterpret_cast<void**>(&scratch));
+  if (se != cudaSuccess) return se;
   const int nblk = (int)std::min<int64_t>(kNormBlocks, std::max<int64_t>(1, (rows + 2047) / 2048));
   { ProfScope ps(TAG_NORM, st);
-  norm_partial_kernel<<<nblk, 256, 0, st>>>(x, rows, F, state, max_acc, scratch[dev]); }
+  norm_partial_kernel<<<nblk, 256, 0, st>>>(x, rows, F, state, max_acc, scratch); }
   { ProfScope ps(TAG_NORM, st);
-  norm_finish_kernel<<<1, 128, 0, st>>>(scratch[dev], nblk, rows, F, state, max_acc); }
+  norm_finish_kernel<<<1, 128, 0, st>>>(scratch, nblk, rows, F, state, max_acc); }
   return cudaGetLastError();
 }
 

@@ -122,20 +122,11 @@ __global__ void shoot_finish_kernel(const float* __restrict__ partial, int nblk,
   loss[0] = (accumulate ? loss[0] : 0.f) + w * t;
 }
 
-static cudaError_t loss_scratch(float** out) {
-  static float* scratch[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
-  if (!scratch[dev]) {
-    cudaError_t e = cudaMalloc(&scratch[dev], sizeof(float) * kLossBlocks);
-    if (e != cudaSuccess) return e;
-  }
-  *out = scratch[dev];
-  return cudaSuccess;
+static cudaError_t loss_scratch(cudaStream_t st, float** out) {
+  return stream_scratch(st, SCRATCH_LOSS, sizeof(float) * kLossBlocks, reinterpret_cast<void**>(out));
 }
 
-static int stream_grid(int64_t n) { return (int)std::min<int64_t>(148 * 8, blocks_for(n, 256)); }
+static int stream_grid(int64_t n) { return (int)std::min<int64_t>((int64_t)device_sm_count() * 8, blocks_for(n, 256)); }
 
 cudaError_t ode_lincomb(const float* x, const float* const* k, const float* coef, int n_terms, int64_t n, float* y,
                         cudaStream_t st) {
@@ -186,7 +177,7 @@ cudaError_t affine_apply_ld(const float* x, int ld_x, int col_x, int64_t rows, i
 cudaError_t shooting_mse(const float* pred, const float* gt, const float* vm, int64_t period, int64_t n, float w,
                          int accumulate, float* loss, float* dpred, cudaStream_t st) {
   float* partial = nullptr;
-  cudaError_t e = loss_scratch(&partial);
+  cudaError_t e = loss_scratch(st, &partial);
   if (e != cudaSuccess) return e;
   const int nblk = (int)std::min<int64_t>(kLossBlocks, blocks_for(n, 2048));
   { ProfScope ps(TAG_LOSS, st);
@@ -199,7 +190,7 @@ cudaError_t shooting_mse(const float* pred, const float* gt, const float* vm, in
 cudaError_t shooting_continuity(const float* a, const float* b, int64_t n, float w, float* loss, float* da,
                                 cudaStream_t st) {
   float* partial = nullptr;
-  cudaError_t e = loss_scratch(&partial);
+  cudaError_t e = loss_scratch(st, &partial);
   if (e != cudaSuccess) return e;
   const int nblk = (int)std::min<int64_t>(kLossBlocks, blocks_for(n, 2048));
   { ProfScope ps(TAG_LOSS, st);

@@ -103,6 +103,8 @@ struct FwdParams {
   float* save_rstd;                       // [rows]
   unsigned long long* trace;              // debug: per-role %globaltimer stamps of CTA 0 (nullptr = off)
   uint32_t stagger_ns;                    // start delay unit that de-phases co-resident CTAs (0 = off)
+  int epi_warps;                          // 8 (two threads per tile row) or 4: mgn_model::knobs
+  int deep_ring;                          // allow the deep-ring variant when the graph has no more tiles than SMs
 };
 
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st);

@@ -1047,22 +1047,13 @@ __global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restric
   *reinterpret_cast<float4*>(d_nf + v * 128 + lane * 4) = s;
 }
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
 }  // namespace
 
-int backward_grid(int n_tiles) { return n_tiles < sm_count() ? n_tiles : sm_count(); }
+int backward_grid(int n_tiles) { return n_tiles < device_sm_count() ? n_tiles : device_sm_count(); }
 
-// ---- debug trace registry (see tc.cuh)
+// ---- debug trace registry (see tc.cuh): compiled in only by `build.py --trace` (-DMGN_ENABLE_TRACE); the product
+//      library has no such global and exports no mgn_debug_trace
+#ifdef MGN_ENABLE_TRACE
 static unsigned long long* g_trace_buf[3] = {nullptr, nullptr, nullptr};
 static int g_trace_skip[3] = {0, 0, 0};
 void set_trace(unsigned long long* d_buf, int kernel, int skip) {
@@ -1077,15 +1068,18 @@ unsigned long long* take_trace(int kernel) {
   g_trace_buf[kernel] = nullptr;
   return b;
 }
+#else
+void set_trace(unsigned long long*, int, int) {}
+unsigned long long* take_trace(int) { return nullptr; }
+#endif
 
 cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(chain::mlp_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)chain::kSmemLaunch);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  cudaError_t ce = configured.run([](int) {
+    return cudaFuncSetAttribute(chain::mlp_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)chain::kSmemLaunch);
+  });
+  if (ce != cudaSuccess) return ce;
   const int grid = backward_grid(p.n_tiles);
   if (grid_out) *grid_out = grid;
   if (grid == 0) return cudaSuccess;
@@ -1097,13 +1091,12 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
 }
 
 cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(input::mlp_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)input::kSmemLaunch);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  cudaError_t ce = configured.run([](int) {
+    return cudaFuncSetAttribute(input::mlp_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)input::kSmemLaunch);
+  });
+  if (ce != cudaSuccess) return ce;
   const int grid = backward_grid(p.n_tiles);
   if (grid_out) *grid_out = grid;
   if (grid == 0) return cudaSuccess;
@@ -1143,13 +1136,12 @@ cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const 
                               float* partial, float* d_raw, cudaStream_t st) {
   if (n_tiles == 0) return cudaSuccess;
   const size_t smem = (size_t)(128 * 129 + 128 * F) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(encoder_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)((128 * 129 + 128 * 64) * sizeof(float)));
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  cudaError_t ce = configured.run([](int) {
+    return cudaFuncSetAttribute(encoder_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((128 * 129 + 128 * 64) * sizeof(float)));
+  });
+  if (ce != cudaSuccess) return ce;
   ProfScope ps(TAG_TC_MISC, st);
   encoder_input_kernel<<<n_tiles, 128, smem, st>>>(dz0, raw, raw_idx, F, w0, M, tile_row_start, partial, d_raw);
   return cudaGetLastError();
@@ -1165,3 +1157,12 @@ cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfl
 
 }  // namespace tc
 }  // namespace mgn
+
+#ifdef MGN_ENABLE_TRACE
+// Debug build only: arm the per-role timestamp trace of the `skip`-th next launch of a tensor-core kernel family
+// (0 forward, 1 backward chain, 2 backward input).  d_buf: 4 * 512 u64, zeroed by the caller.
+extern "C" int32_t mgn_debug_trace(void* d_buf, int32_t kernel, int32_t skip) {
+  mgn::tc::set_trace(static_cast<unsigned long long*>(d_buf), kernel, skip);
+  return MGN_OK;
+}
+#endif

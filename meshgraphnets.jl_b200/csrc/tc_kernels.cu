@@ -13,8 +13,6 @@
 //     CSR segmented sum (a11) from shared memory, so the per-edge message never touches HBM.
 // Two CTAs are resident per SM (<= 113 KB smem, 128 TMEM columns each) so one CTA's epilogue
 // overlaps the other's MMAs.
-#include <cstdlib>
-
 #include "tc.cuh"
 #include "tc_ptx.cuh"
 
@@ -555,21 +553,12 @@ cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat
   return cudaGetLastError();
 }
 
-// Epilogue warps per CTA: 8 (two threads per tile row) unless MGN_FWD_EPI_WARPS=4 selects the one-thread-per-row layout.
-static int fwd_epilogue_warps() {
-  static int ew = 0;
-  if (ew == 0) {
-    const char* e = getenv("MGN_FWD_EPI_WARPS");
-    ew = (e && atoi(e) == 4) ? 4 : 8;
-  }
-  return ew;
-}
-
+// Variant selection comes from the model handle (FwdParams::epi_warps / deep_ring / stagger_ns, frozen at
+// mgn_model_create); the opt-in shared-memory limits are set once per device.
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
   if (p.n_tiles == 0) return cudaSuccess;
-  static bool configured = false;
-  static int n_sm = 148;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  cudaError_t ce = configured.run([](int) {
     cudaError_t e = cudaSuccess;
     auto set = [&](const void* f, uint32_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -577,32 +566,18 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
     set((const void*)mlp_fwd_kernel<4, kRingShared, 1>, Lay<kRingShared>::kLaunch);
     set((const void*)mlp_fwd_kernel<8, kRingShared, 1>, Lay<kRingShared>::kLaunch);
     set((const void*)mlp_fwd_kernel<8, kRingDeep, 4>, Lay<kRingDeep>::kLaunch);
-    if (e != cudaSuccess) return e;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
-  }
+    return e;
+  });
+  if (ce != cudaSuccess) return ce;
+  const int n_sm = device_sm_count();
   const int grid = p.n_tiles < 2 * n_sm ? p.n_tiles : 2 * n_sm;
   ProfScope ps(TAG_TC_MLP_FWD, st);
   FwdParams q = p;
   q.trace = take_trace(0);
-  {
-    static int stagger = -1;
-    if (stagger < 0) {
-      const char* e = getenv("MGN_FWD_STAGGER_NS");
-      stagger = e ? atoi(e) : 0;
-    }
-    q.stagger_ns = grid > n_sm ? (uint32_t)stagger : 0u;
-  }
-  static int deep_ok = -1;  // MGN_FWD_DEEP_RING=0 disables the deep-ring variant
-  if (deep_ok < 0) {
-    const char* e = getenv("MGN_FWD_DEEP_RING");
-    deep_ok = (e && atoi(e) == 0) ? 0 : 1;
-  }
-  if (fwd_epilogue_warps() == 4)
+  if (grid <= n_sm) q.stagger_ns = 0u;
+  if (p.epi_warps == 4)
     mlp_fwd_kernel<4, kRingShared, 1><<<grid, 32 * 6, Lay<kRingShared>::kLaunch, st>>>(q);
-  else if (deep_ok && p.n_tiles <= n_sm)
+  else if (p.deep_ring && p.n_tiles <= n_sm)
     mlp_fwd_kernel<8, kRingDeep, 4><<<grid, 32 * 13, Lay<kRingDeep>::kLaunch, st>>>(q);
   else
     mlp_fwd_kernel<8, kRingShared, 1><<<grid, 32 * 10, Lay<kRingShared>::kLaunch, st>>>(q);

@@ -101,6 +101,9 @@ void fill_layers(const mgn_model* m, size_t mi, const float* params, const TcWor
   for (int l = 0; l < kMaxLayers - 1; ++l) p.save_h[l] = training ? w.saves[mi].h[l] : nullptr;
   p.save_xhat = training ? w.saves[mi].xhat : nullptr;
   p.save_rstd = training ? w.saves[mi].rstd : nullptr;
+  p.epi_warps = m->knobs.fwd_epi_warps;
+  p.deep_ring = m->knobs.fwd_deep_ring;
+  p.stagger_ns = (uint32_t)m->knobs.fwd_stagger_ns;
 }
 
 // Scratch of the backward pass, placed after the forward workspace.

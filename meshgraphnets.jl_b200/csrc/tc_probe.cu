@@ -3,11 +3,19 @@
 //   mode 1: D[128][128] = A[K][128]^T * B[K][128]      (A, B row-major, both MN-major operands,
 //                                                        the weight-gradient form dW = dZ^T H)
 // with K a multiple of 64 (<= 256).  Exercised by tests/test_gpu_tc_probe.py against torch.
+// NOT part of the product library: built on its own as libmgn_b200_probe.so (build.py), loaded by that test only.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include "tc.cuh"
 
 namespace mgn {
+// the probe library is self-contained: its own copies of the two error helpers of abi.cu
+static thread_local std::string g_probe_error;
+void set_error(const std::string& msg) { g_probe_error = msg; }
+int32_t fail(int32_t code, const std::string& msg) {
+  g_probe_error = msg;
+  return code;
+}
 namespace {
 using namespace tc;
 
@@ -106,9 +114,3 @@ extern "C" int32_t mgn_debug_umma_probe(const void* d_a, const void* d_b, float*
   return MGN_OK;
 }
 
-// Debug: arm the per-role timestamp trace of the `skip`-th next launch of a tensor-core kernel family
-// (0 forward, 1 backward chain, 2 backward input).  d_buf: 4 * 512 u64, zeroed by the caller.
-extern "C" int32_t mgn_debug_trace(void* d_buf, int32_t kernel, int32_t skip) {
-  mgn::tc::set_trace(static_cast<unsigned long long*>(d_buf), kernel, skip);
-  return MGN_OK;
-}

@@ -128,8 +128,12 @@ class DistExchange:
     """Transport over torch.distributed (one process per GPU): a single all_to_all_single per exchange with
     static split sizes known to both sides from the partition plan (NCCL over NVLink; gloo in CPU tests)."""
 
-    def __init__(self, part: LocalGraph, world, device):
+    def __init__(self, part: LocalGraph, world, device, model: Model = None):
+        """`model` fixes the row widths (halo_row_bytes of the latent / of the gradient) for ranks that only receive in
+        one direction (possible with one-way edge lists); without it the width is read off the first send buffer."""
         self.rank, self.world, self.device = part.rank, world, device
+        self.width = None if model is None else {"fwd": model.halo_row_bytes(_lib.HALO_LATENT),
+                                                 "bwd": model.halo_row_bytes(_lib.HALO_GRAD)}
         self.n_send = [len(part.send_rows.get(p, ())) for p in range(world)]   # forward: owned rows -> peers
         self.n_recv = [len(part.recv_rows.get(p, ())) for p in range(world)]   # forward: peers' rows -> my halo
 
@@ -137,7 +141,15 @@ class DistExchange:
         import torch.distributed as dist
         mine = sends.get(self.rank, {})
         n_in, n_out = (self.n_send, self.n_recv) if direction == "fwd" else (self.n_recv, self.n_send)
-        width = next(iter(mine.values())).shape[1] if mine else 1
+        if self.width is not None:
+            width = self.width[direction]
+        elif mine:
+            width = next(iter(mine.values())).shape[1]
+        elif sum(n_out) == 0:
+            width = 1                        # nothing moves either way on this rank
+        else:
+            raise _lib.MgnError(-1, "DistExchange: this rank sends nothing in this direction, so the row width is "
+                                    "unknown - construct it with model=...")
         chunks = [mine[p] for p in range(self.world) if n_in[p]]
         inp = torch.cat(chunks) if chunks else torch.empty((0, width), dtype=torch.uint8, device=self.device)
         outp = torch.empty((sum(n_out), width), dtype=torch.uint8, device=self.device)

@@ -11,6 +11,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from ._lib import MgnError
 from .graph import build_graph
 from .shooting import RK_TABLEAUS, DeviceAlgebra
 
@@ -86,20 +87,56 @@ def _rollout_params(mgn, initial_state, fields, meta, target_fields, target_dict
             receivers, val_mask, inflow_mask, saves[1] - saves[0])
 
 
+def _step_plan(start, stop, dt, saves):
+    """The fixed-step grid of ``solve(prob, solver; adaptive=false, dt=dt, saveat=saves)`` over (start, stop)
+    (src/solve.jl:62): the integrator advances in steps of ``dt`` from ``start`` and a save time must coincide with a
+    grid point (interpolated saves are OrdinaryDiffEq's dense output: out of scope, so they raise instead of silently
+    landing on the wrong physical time).  ``dt = None`` is the ``tstops = saves`` branch (:60): one step per save
+    interval.  Returns [(n_sub, h)] per save interval, preceded by the (start -> saves[0]) lead-in."""
+    saves = [float(np.float32(v)) for v in saves]
+    if len(saves) < 2:
+        raise MgnError(-1, "rollout needs at least two save times (saves[2] - saves[1] is the inflow data spacing)")
+    start = saves[0] if start is None else float(np.float32(start))
+    if start > saves[0] + 1e-6 * max(1.0, abs(saves[0])) or (stop is not None and saves[-1] > float(stop) * (1 + 1e-6) + 1e-12):
+        raise MgnError(-1, f"save times {saves[0]}..{saves[-1]} are outside the integration interval ({start}, {stop})")
+    plan = []
+    for a, b in zip([start] + saves[:-1], saves):
+        span = b - a
+        if span < -1e-9:
+            raise MgnError(-1, "save times must be increasing")
+        if dt is None:
+            plan.append((1 if span > 1e-9 * max(1.0, abs(b)) else 0, np.float32(span)))
+            continue
+        n = int(round(span / float(dt)))
+        if abs(n * float(dt) - span) > 1e-4 * float(dt) + 1e-7 * max(1.0, abs(b)):
+            raise MgnError(-1, f"the fixed step dt = {dt} does not divide the save interval ({a}, {b}): saves between "
+                               "grid points need dense output, which this mirror does not provide")
+        plan.append((n, np.float32(dt)))
+    return start, saves, plan
+
+
+def _integrate(f, x, start, plan, solver, on_save):
+    t = np.float32(start)
+    for k, (n_sub, h) in enumerate(plan):
+        for _ in range(n_sub):
+            x = rk_step(f, x, t, h, solver)
+            t = np.float32(t + h)
+        on_save(k, x)
+    return x
+
+
 def rollout(mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
             receivers, val_mask, inflow_mask, data, start, stop, dt, saves, solver="euler"):
-    """src/solve.jl:42-68 with ``solve(prob, Euler(); adaptive=false, dt=dt, saveat=saves)``.
+    """src/solve.jl:42-68 with ``solve(prob, solver; adaptive=false, dt=dt, saveat=saves)`` over (start, stop): fixed
+    steps of ``dt`` (several per save interval when dt divides it), inflow data indexed by the sub-step's own time.
     Returns (list of saved states, times)."""
     x = torch.cat([initial_state[f] for f in target_fields], dim=1).clone()
     p = _rollout_params(mgn, initial_state, fields, meta, target_fields, target_dict, node_type, edge_feats, senders,
                         receivers, val_mask, inflow_mask, data, saves)
-    sol, ts = [x.clone()], [float(saves[0])]
-    for i in range(len(saves) - 1):
-        t = np.float32(saves[i])  # tstops = saves: the integrator lands on the save times
-        x = rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), x, t, dt, solver)
-        sol.append(x.clone())
-        ts.append(float(saves[i + 1]))
-    return sol, ts
+    start, saves_f, plan = _step_plan(start, stop, dt, saves)
+    sol = []
+    _integrate(lambda xx, tt: ode_func_eval(xx, p, tt), x, start, plan, solver, lambda k, xx: sol.append(xx.clone()))
+    return sol, saves_f
 
 
 class CapturedRollout:
@@ -118,19 +155,19 @@ class CapturedRollout:
         self._keep = p      # the graph holds raw addresses: every tensor it reads must outlive it (e.g. the uint8 mask)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        start, saves_f, plan = _step_plan(start, stop, dt, saves)
+        h0 = next((h for n, h in plan if n > 0), np.float32(saves[1] - saves[0]))
         with torch.cuda.stream(side):             # warm-up: allocations and first-use scratch happen outside capture
             for _ in range(2):
-                rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), self.x0.clone(), np.float32(saves[0]), dt, solver)
+                rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), self.x0.clone(), np.float32(start), h0, solver)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            x = self.x0.clone()
-            self.sol = [x.clone()]
-            for i in range(len(saves) - 1):
-                x = rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), x, np.float32(saves[i]), dt, solver)
-                self.sol.append(x.clone())
-        self.ts = [float(s) for s in saves]
+            self.sol = []
+            _integrate(lambda xx, tt: ode_func_eval(xx, p, tt), self.x0.clone(), start, plan, solver,
+                       lambda k, xx: self.sol.append(xx.clone()))
+        self.ts = saves_f
 
     def replay(self, initial_state=None):
         if initial_state is not None:

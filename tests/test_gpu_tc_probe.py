@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _probe(pkg, a, b, K, mode):
-    lib = pkg.load()
+    import os
+    lib = C.CDLL(os.path.join(os.path.dirname(pkg.LIB_PATH), "libmgn_b200_probe.so"))   # test-only library
     fn = lib.mgn_debug_umma_probe
     fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
     fn.restype = C.c_int32

@@ -55,7 +55,7 @@ def main():
     mode = pkg.COMPUTE_BF16 if args.mode == "bf16" else pkg.COMPUTE_FP32
     model, ps, _ = pkg.build_model(4, 3, 3, args.mps, 128, 2, device=dev, compute_mode=mode)
     pm = pkg.PartitionedModel(model, part, nf, ef, device=dev)
-    ex = pkg.DistExchange(part, world, dev) if world > 1 else pkg.LocalExchange()
+    ex = pkg.DistExchange(part, world, dev, model) if world > 1 else pkg.LocalExchange()
     halo_rows = sum(len(v) for v in part.recv_rows.values())
 
     def step():

@@ -28,7 +28,7 @@ mask = dev(orc.node_mask(np.tile(nt, B), [0, 5]))
 model, ps, _ = pkg.build_model(9, 2, 2, 15, 128, 2, compute_mode=pkg.COMPUTE_BF16)
 graph = pkg.FeatureGraph(nf, ef, dev(s), dev(r))
 mgn = pkg.GraphNetwork(model, ps, None, None, None, None)
-lib = pkg.load()
+lib = pkg.load()   # needs the debug build: python meshgraphnets.jl_b200/build.py --trace
 lib.mgn_debug_trace.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
 for _ in range(2):
     pkg.step_(mgn, graph, tgt, mask)
