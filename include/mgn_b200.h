@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MGN_ABI_VERSION 1
+#define MGN_ABI_VERSION 2
 
 enum {
   MGN_OK = 0,
@@ -192,6 +192,50 @@ int32_t mgn_adam_step_device(float* d_params, const float* d_grads, float* d_m, 
                              float lr, float beta1, float beta2, float eps, void* d_state16,
                              void* stream);
 
+/* ------------------------------------------------------------------ multi-GPU transport (NEW: SURVEY 8b mgn_dp_*, 8e) */
+/* The reference is single device (src/MeshGraphNets.jl:257).  One process (or Julia task) per GPU; NCCL over NVLink is
+ * loaded at run time (dlopen "libnccl.so.2": no link-time dependency, MGN_ERR_UNSUPPORTED when absent).  Bootstrap:
+ * rank 0 calls mgn_dp_unique_id and hands the 128 bytes to the other ranks by any means (MPI.jl, a file, a socket, or
+ * torch.distributed in the Python mirror); every rank then calls mgn_dp_init on ITS device.  The collectives below only
+ * enqueue on `stream` and are CUDA-graph capturable. */
+#define MGN_DP_UNIQUE_ID_BYTES 128
+typedef struct mgn_comm mgn_comm;
+enum { MGN_DP_SUM = 0, MGN_DP_MEAN = 1 };
+int32_t mgn_dp_unique_id(void* h_id128);
+int32_t mgn_dp_init(const void* h_id128, int32_t rank, int32_t world, mgn_comm** out);
+int32_t mgn_dp_finalize(mgn_comm* c);
+int32_t mgn_dp_rank(const mgn_comm* c, int32_t* rank, int32_t* world);
+/* In-place all-reduce of a flat Float32 buffer: the data-parallel gradient of src/MeshGraphNets.jl:364-378 run as
+ * batch-P SGD (MEAN), or loss / gradient of interval-sharded MultipleShooting and of a partitioned mesh (SUM). */
+int32_t mgn_dp_allreduce(mgn_comm* c, float* d_buf, int64_t n, int32_t op, void* stream);
+/* Online-normaliser state after a step in which every rank accumulated its own window on top of the common d_prev:
+ * state = prev + sum over ranks of (state_r - prev); n_floats = 2 * features + 2.  d_prev may alias nothing. */
+int32_t mgn_dp_allreduce_normaliser(mgn_comm* c, float* d_state, const float* d_prev, int32_t n_floats, void* stream);
+/* Halo exchange of a partitioned mesh (one per message-passing step): rank p receives
+ * h_send_rows[p] rows of row_bytes bytes from d_send (packed per peer in rank order) and this rank receives
+ * h_recv_rows[p] rows from rank p into d_recv (same packing): grouped ncclSend / ncclRecv. */
+int32_t mgn_halo_exchange(mgn_comm* c, const void* d_send, const int64_t* h_send_rows, void* d_recv,
+                          const int64_t* h_recv_rows, int64_t row_bytes, void* stream);
+
+/* Optimisers.update fused with the gradient all-reduce, bucketed and overlapped with the backward pass
+ * (src/MeshGraphNets.jl:374-378).  mgn_backward_dp is mgn_backward plus, per bucket of consecutive MLPs
+ * (gradients complete in reverse parameter order: decoder first, encoders last): as soon as a bucket's gradients are
+ * final, on an internal side stream, (1) ncclAllReduce(avg) over `comm` when comm != NULL, (2) the Adam update of that
+ * bucket's parameters when adam != NULL (its own parameters are no longer read by the rest of the backward pass).
+ * `stream` joins the side stream before the call returns control to later work on `stream`.  With comm == NULL and
+ * adam == NULL it is mgn_backward.  d_params is updated in place when adam != NULL. */
+typedef struct mgn_adam_config {
+  float lr, beta1, beta2, eps;
+  float* d_m;       /* [P] first moments  */
+  float* d_v;       /* [P] second moments */
+  void* d_state16;  /* {int64 step; float c1; float c2}, see mgn_adam_step_device */
+} mgn_adam_config;
+int32_t mgn_backward_dp(const mgn_model* m, const mgn_graph* g, float* d_params, const float* d_nf, const float* d_ef,
+                        const float* d_dout, float* d_dparams, float* d_dnf, void* d_workspace, size_t workspace_bytes,
+                        mgn_comm* comm, const mgn_adam_config* adam, int32_t n_buckets, void* stream);
+/* Frees the library's per-(device, stream) scratch buffers; handles stay valid. */
+int32_t mgn_library_release(void);
+
 /* ------------------------------------------------------------------ measurement hooks (bench.py) */
 /* Counts every kernel launch of the library and brackets the launches of one kernel family
  * (`tag`, see mgn_profile_tag_name; -1 = count only) with CUDA events on their own stream.
@@ -207,7 +251,8 @@ int32_t mgn_profile_tag_name(int32_t tag, char* buf, size_t n);
  * num_acc] (2F+2 floats).  mgn_norm_online_update is the accumulate branch of the callable
  * (src/graph.jl:80,84,93; src/strategies.jl:399-410); it is skipped on-device once
  * num_acc >= max_acc.  d_x is [M][F], F <= 64.  Deterministic two-stage sum; the first call on a device allocates a
- * 64 KB scratch (do it once outside CUDA-graph capture); updates on one device must not run concurrently. */
+ * 64 KB scratch private to (device, stream) - also legal inside a stream capture; a captured graph keeps the scratch of its
+ * capture stream, so replay one instance of it at a time. */
 int32_t mgn_norm_online_update(const float* d_x, int64_t rows, int32_t features, float* d_state,
                                float max_acc, void* stream);
 /* y = (x - mean)/std (inverse == 0) or y = x*std + mean (inverse != 0, inverse_data at
@@ -254,7 +299,7 @@ int32_t mgn_affine_apply_ld(const float* d_x, int32_t ld_x, int32_t col_x, int64
  * train_loss(::MultipleShooting)  <- src/strategies.jl:367-378:  with e = (gt - pred).^2 .* val_mask over n_saves saved
  * states of mask_elems = N*S values each,  d_loss[0] = (accumulate ? d_loss[0] : 0) + weight * sum(e)  (weight =
  * 1 / (n_saves * mask_elems) gives `mean`), and d_dpred = d loss / d pred.  Fixed summation order (deterministic).
- * The first call on a device allocates 1 KB of scratch (do it once outside CUDA-graph capture). */
+ * Scratch (1 KB) is private to (device, stream), allocated on first use - also legal inside a stream capture. */
 int32_t mgn_shooting_mse(const float* d_pred, const float* d_gt, const float* d_val_mask, int64_t n_saves,
                          int64_t mask_elems, float weight, int32_t accumulate, float* d_loss, float* d_dpred,
                          void* stream);

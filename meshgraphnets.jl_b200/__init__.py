@@ -11,14 +11,14 @@ workloads.py     synthetic BASELINE workloads + the driver's mask helpers (src/M
 parallel.py      data-parallel plumbing (window sharding, gradient / normaliser all-reduce)
 """
 from ._lib import COMPUTE_BF16, COMPUTE_FP32, LIB_PATH, MgnError, load  # noqa: F401
-from .core import (Adam, FeatureGraph, GraphIndex, GraphNetwork, Model, NormaliserOfflineMeanStd,  # noqa: F401
+from .core import (Adam, FeatureGraph, step_dp_, GraphIndex, GraphNetwork, Model, NormaliserOfflineMeanStd,  # noqa: F401
                    NormaliserOfflineMinMax, NormaliserOnline, build_model, edge_features, init_params,
                    inverse_data, mse_reduce, one_hot, parse_edges, profile_begin, profile_end, profile_tag,
                    shift_one_based, step_,
                    triangles_to_edges)
 from .graph import build_graph, create_base_graph  # noqa: F401
-from .parallel import allreduce_mean_, allreduce_normaliser_, allreduce_sum_, shard_windows  # noqa: F401
-from .partition import (DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
+from .parallel import Communicator, allreduce_mean_, allreduce_normaliser_, allreduce_sum_, shard_windows  # noqa: F401
+from .partition import (AbiExchange, DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
                         build_partition_rank,
                         masked_mse_partial, partition_bounds, run_partitioned_step)
 from ._lib import NORM_FORWARD, NORM_FORWARD_VJP, NORM_INVERSE, NORM_INVERSE_VJP  # noqa: F401

@@ -16,6 +16,8 @@ STAGE_ENCODE, STAGE_DECODE = -1, -2
 HALO_LATENT, HALO_GRAD = 0, 1
 ROWS_PACK, ROWS_UNPACK, ROWS_ADD, ROWS_PACK_ZERO = 0, 1, 2, 3
 NORM_FORWARD, NORM_INVERSE, NORM_FORWARD_VJP, NORM_INVERSE_VJP = 0, 1, 2, 3
+DP_SUM, DP_MEAN = 0, 1
+DP_UNIQUE_ID_BYTES = 128
 
 
 class MgnError(RuntimeError):
@@ -30,6 +32,12 @@ class ModelConfig(C.Structure):
         ("latent", C.c_int32), ("mps", C.c_int32), ("hidden_layers", C.c_int32),
         ("ln_eps", C.c_float), ("compute_mode", C.c_int32),
     ]
+
+
+class AdamConfig(C.Structure):
+    """mgn_adam_config of include/mgn_b200.h (mgn_backward_dp)."""
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("d_m", C.c_void_p), ("d_v", C.c_void_p), ("d_state16", C.c_void_p)]
 
 
 class ParamEntry(C.Structure):
@@ -80,6 +88,15 @@ SIGNATURES = {
     "mgn_affine_apply_ld": [_p, _i32, _i32, _i64, _i32, _f32, _f32, _p, _i32, _i32, _p],
     "mgn_shooting_mse": [_p, _p, _p, _i64, _i64, _f32, _i32, _p, _p, _p],
     "mgn_shooting_continuity": [_p, _p, _i64, _f32, _p, _p, _p],
+    "mgn_dp_unique_id": [_p],
+    "mgn_dp_init": [_p, _i32, _i32, C.POINTER(_p)],
+    "mgn_dp_finalize": [_p],
+    "mgn_dp_rank": [_p, C.POINTER(_i32), C.POINTER(_i32)],
+    "mgn_dp_allreduce": [_p, _p, _i64, _i32, _p],
+    "mgn_dp_allreduce_normaliser": [_p, _p, _p, _i32, _p],
+    "mgn_halo_exchange": [_p, _p, C.POINTER(_i64), _p, C.POINTER(_i64), _i64, _p],
+    "mgn_backward_dp": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p, C.POINTER(AdamConfig), _i32, _p],
+    "mgn_library_release": [],
 }
 
 _lib = None

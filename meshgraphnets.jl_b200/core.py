@@ -473,6 +473,40 @@ def step_(mgn: GraphNetwork, graph: FeatureGraph, target, mask, loss_function=ms
     return (gs,), loss
 
 
+def step_dp_(mgn: GraphNetwork, graph: FeatureGraph, target, mask, opt=None, opt_state=None, comm=None, n_buckets=4,
+             index_base=1):
+    """step! (src/strategies.jl:421) fused with what the driver does with its result (src/MeshGraphNets.jl:374-378):
+    forward, loss and mgn_backward_dp - the backward pass whose gradient buckets are all-reduced (mean over the ranks of
+    `comm`, a parallel.Communicator) and fed to Adam on a side stream while the rest of the backward pass still runs.
+    With `opt` the parameters are updated in place.  Returns ((gs,), loss) like step_."""
+    model: Model = mgn.model
+    target = _dev_f32(target, "target")
+    mask = _dev_i32(mask, "mask")
+    out = model.forward(graph, mgn.ps, training=True)
+    loss = torch.empty(1, dtype=torch.float32, device=out.device)
+    dout = torch.empty_like(out)
+    call("mgn_loss_mse_masked", _ptr(out), _ptr(target), out.shape[0], out.shape[1], _ptr(mask),
+         mask.shape[0], int(index_base), _ptr(loss), _ptr(dout), _stream())
+    gi = graph.index
+    ws = model.workspace(gi, True, 0)
+    nf = _dev_f32(graph.node_features, "node_features")
+    ef = _dev_f32(graph.edge_features, "edge_features")
+    key = ("_dps", mgn.ps.data_ptr())
+    dps = model.__dict__.get(key)
+    if dps is None or dps.numel() != model.n_params:
+        dps = torch.empty(model.n_params, dtype=torch.float32, device=nf.device)
+        model.__dict__[key] = dps
+    cfg = None
+    if opt is not None:
+        opt_state["t"] += 1
+        cfg = _lib.AdamConfig(opt.eta, opt.beta[0], opt.beta[1], opt.epsilon, opt_state["m"].data_ptr(),
+                              opt_state["v"].data_ptr(), opt_state["dev"].data_ptr())
+    call("mgn_backward_dp", model._h, gi._h, _ptr(mgn.ps), _ptr(nf), _ptr(ef), _ptr(dout), _ptr(dps), None, _ptr(ws),
+         ws.numel(), comm._h if comm is not None else None, C.byref(cfg) if cfg is not None else None, int(n_buckets),
+         _stream())
+    return (dps,), loss
+
+
 class Adam:
     """Optimisers.Adam + Optimisers.setup/update as used at src/MeshGraphNets.jl:288,374-378."""
 

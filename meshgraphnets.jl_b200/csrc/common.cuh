@@ -200,6 +200,11 @@ cudaError_t adam_step(float* p, const float* g, float* m, float* v, int64_t n, f
                       float b2, float eps, int64_t t, cudaStream_t st);
 cudaError_t adam_step_device(float* p, const float* g, float* m, float* v, int64_t n, float lr,
                              float b1, float b2, float eps, void* state16, cudaStream_t st);
+// The two halves of adam_step_device, for bucketed updates: advance the device-side step counter once, then update
+// any number of parameter ranges with it.
+cudaError_t adam_tick(void* state16, float b1, float b2, cudaStream_t st);
+cudaError_t adam_apply_range(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                             float eps, const void* state16, cudaStream_t st);
 cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
                                cudaStream_t st);
 cudaError_t norm_online_apply(const float* x, int64_t rows, int F, const float* state,
@@ -228,19 +233,26 @@ int32_t build_graph_index(mgn_graph* g, const int32_t* d_senders, const int32_t*
                           cudaStream_t st);
 
 // ---- orchestration: pipeline.cu --------------------------------------------------------------
+// Notified by the backward pass, on the host, right after the launches that FINISH the gradient of MLP `mi` have been
+// enqueued on the stream; MLPs finish in descending index order (decoder first), so mlp_done(mi) means that the flat
+// gradient range from MLP mi to the end is final on the stream (dp.cu buckets the all-reduce / Adam update on it).
+struct GradHook {
+  virtual int32_t mlp_done(size_t mi) = 0;
+  virtual ~GradHook() = default;
+};
 int32_t workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training, size_t* bytes);
 int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                 const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
                 cudaStream_t st);
 int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                  const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                 size_t ws_bytes, cudaStream_t st);
+                 size_t ws_bytes, cudaStream_t st, GradHook* hook = nullptr);
 int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                       const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
                       cudaStream_t st);
 int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                        const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                       size_t ws_bytes, int stage, cudaStream_t st);
+                       size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook = nullptr);
 int32_t halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
                   int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st);
 // Row pack / unpack / add between a [N][row_elems] tensor of elem_bytes-wide elements and a contiguous buffer.

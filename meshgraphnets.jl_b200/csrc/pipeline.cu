@@ -233,9 +233,10 @@ int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* param
 
 int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                        const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                       size_t ws_bytes, int stage, cudaStream_t st) {
+                       size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook) {
   if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
-    return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, stage, st);
+    return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, stage, st, hook);
+  auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi) : MGN_OK; };
   Workspace w;
   layout(m, g, true, ws, w);
   if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_backward");
@@ -248,6 +249,7 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
     // Decoder: d_nf = d(out)/d(nf[mps])
     MGN_CUDA_TRY(mlp_backward(m->mlps[di], params, dparams, op1(w.nf[mps], nullptr, D, D), N,
                               w.saved[di], dout, m->cfg.out_dim, nullptr, 0, nullptr, w, w.d_nf, st));
+    MGN_TRY(done(di));
   }
   for (int k = mps - 1; k >= 0; --k) {
     if (!all && stage != k) continue;
@@ -259,6 +261,7 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
     xn.s[1] = {w.agg[k], nullptr, D, D};
     MGN_CUDA_TRY(mlp_backward(m->mlps[3 + 2 * k], params, dparams, xn, N, w.saved[3 + 2 * k], w.d_nf,
                               D, nullptr, 0, nullptr, w, w.dxn, st));
+    MGN_TRY(done(3 + 2 * k));
     // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
     Operand xe{};
     xe.nseg = 3;
@@ -268,6 +271,7 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
     MGN_CUDA_TRY(mlp_backward(m->mlps[2 + 2 * k], params, dparams, xe, E, w.saved[2 + 2 * k],
                               d_ef_valid ? w.d_ef : nullptr, D, w.dxn + D, 2 * D, g->recv_csr, w,
                               w.dxe, st));
+    MGN_TRY(done(2 + 2 * k));
     // d_nf[k] = d_nf[k+1] + d(node MLP)/d(nf) + gathers' adjoints (receiver: CSR, sender: CSC)
     MGN_CUDA_TRY(node_grad_gather(w.d_nf, w.dxn, 2 * D, w.dxe, g->row_ptr, g->col_ptr, g->csc_slot,
                                   N, D, w.d_nf, st));
@@ -283,9 +287,11 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
       const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
     }
+    MGN_TRY(done(1));
     MGN_CUDA_TRY(mlp_backward(m->mlps[0], params, dparams,
                               op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N, w.saved[0], w.d_nf, D,
                               nullptr, 0, nullptr, w, dnf, st));
+    MGN_TRY(done(0));
   }
   return MGN_OK;
 }
@@ -298,8 +304,8 @@ int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, con
 
 int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                  const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                 size_t ws_bytes, cudaStream_t st) {
-  return backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st);
+                 size_t ws_bytes, cudaStream_t st, GradHook* hook) {
+  return backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st, hook);
 }
 
 // Rows of the node latent / its gradient, for the halo exchange of graph-partitioned meshes.

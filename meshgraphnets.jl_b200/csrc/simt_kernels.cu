@@ -841,6 +841,20 @@ cudaError_t adam_step_device(float* p, const float* g, float* m, float* v, int64
   return cudaGetLastError();
 }
 
+cudaError_t adam_tick(void* state16, float b1, float b2, cudaStream_t st) {
+  ProfScope ps(TAG_ADAM, st);
+  adam_tick_kernel<<<1, 1, 0, st>>>(static_cast<AdamState*>(state16), b1, b2);
+  return cudaGetLastError();
+}
+
+cudaError_t adam_apply_range(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2,
+                             float eps, const void* state16, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  ProfScope ps(TAG_ADAM, st);
+  adam_dev_kernel<<<blocks_for(n, 256), 256, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, static_cast<const AdamState*>(state16));
+  return cudaGetLastError();
+}
+
 cudaError_t norm_online_update(const float* x, int64_t rows, int F, float* state, float max_acc,
                                cudaStream_t st) {
   if (F > kNormMaxF) return cudaErrorInvalidValue;

@@ -15,14 +15,14 @@ int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, 
                    cudaStream_t st);
 int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                     const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                    size_t ws_bytes, cudaStream_t st);
+                    size_t ws_bytes, cudaStream_t st, GradHook* hook = nullptr);
 int32_t tc_backward_scratch_bytes(const mgn_model* m, const mgn_graph* g, size_t* bytes);
 int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                          const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
                          cudaStream_t st);
 int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                           const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                          size_t ws_bytes, int stage, cudaStream_t st);
+                          size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook = nullptr);
 int32_t tc_halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
                      int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st);
 

@@ -408,7 +408,8 @@ int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const floa
 
 int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                           const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                          size_t ws_bytes, int stage, cudaStream_t st) {
+                          size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook) {
+  auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi) : MGN_OK; };
   if (!g->tiles_ok)
     return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
   TcWorkspace w;
@@ -442,6 +443,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     p.sink[0] = SINK_ADD_F32;
     p.f32_dst[0] = b.d_nf;
     MGN_TRY(run_input(c, di, p, pc));
+    MGN_TRY(done(di));
   }
   for (int k = mps - 1; k >= 0; --k) {
     if (!all && stage != k) continue;
@@ -462,6 +464,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.sink[1] = SINK_ADD_F32;  // gradient of the aggregated messages
       p.f32_dst[1] = b.d_agg;
       MGN_TRY(run_input(c, mi, p, pc));
+      MGN_TRY(done(mi));
     }
     if (E > 0) {  // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
       const size_t mi = 2 + 2 * k;
@@ -493,6 +496,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       const int64_t lo = m->mlps[2 + 2 * k].w_off[0], hi = m->mlps[3 + 2 * k].w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + lo, 0, sizeof(float) * (hi - lo), st));
     }
+    MGN_TRY(done(2 + 2 * k));
   }
   if (all || stage == MGN_STAGE_ENCODE) {
     const MlpLayout& L = m->mlps[1];
@@ -504,17 +508,19 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
     }
+    MGN_TRY(done(1));
     Pieces pc{};
     MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr, pc));
     MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf, pc));
+    MGN_TRY(done(0));
   }
   return MGN_OK;
 }
 
 int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                     const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                    size_t ws_bytes, cudaStream_t st) {
-  return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st);
+                    size_t ws_bytes, cudaStream_t st, GradHook* hook) {
+  return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st, hook);
 }
 
 int32_t tc_halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,

@@ -162,6 +162,33 @@ class DistExchange:
         return {self.rank: recv}
 
 
+class AbiExchange:
+    """The same exchange through the library's own NCCL transport (mgn_halo_exchange: grouped ncclSend / ncclRecv on the
+    caller's stream) - the path a Julia caller has.  `comm` is a parallel.Communicator."""
+
+    def __init__(self, part: LocalGraph, world, comm, model: Model):
+        self.rank, self.world, self.comm = part.rank, world, comm
+        self.width = {"fwd": model.halo_row_bytes(_lib.HALO_LATENT), "bwd": model.halo_row_bytes(_lib.HALO_GRAD)}
+        self.n_send = [len(part.send_rows.get(p, ())) for p in range(world)]
+        self.n_recv = [len(part.recv_rows.get(p, ())) for p in range(world)]
+
+    def __call__(self, sends, direction):
+        mine = sends.get(self.rank, {})
+        n_in, n_out = (self.n_send, self.n_recv) if direction == "fwd" else (self.n_recv, self.n_send)
+        width = self.width[direction]
+        dev = next(iter(mine.values())).device if mine else torch.device("cuda", torch.cuda.current_device())
+        chunks = [mine[p] for p in range(self.world) if n_in[p]]
+        inp = torch.cat(chunks) if chunks else torch.empty((0, width), dtype=torch.uint8, device=dev)
+        outp = torch.empty((sum(n_out), width), dtype=torch.uint8, device=dev)
+        self.comm.halo_exchange(inp, n_in, outp, n_out, width)
+        recv, off = {}, 0
+        for p in range(self.world):
+            if n_out[p]:
+                recv[p] = outp[off:off + n_out[p]]
+                off += n_out[p]
+        return {self.rank: recv}
+
+
 class PartitionedModel:
     """One rank's share of a partitioned mesh: the local FeatureGraph, the exchange plan on the device and the
     stage-wise forward / backward of include/mgn_b200.h."""

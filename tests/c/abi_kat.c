@@ -103,6 +103,26 @@ int main(void) {
     }
     printf("devices: %d\n", ndev);
   }
+  /* multi-GPU transport (SURVEY 8b mgn_dp_*): the symbols link from C; argument checking works without a device or
+   * NCCL, and a world of one rank is a no-op that needs neither */
+  {
+    mgn_comm* comm = NULL;
+    unsigned char id[MGN_DP_UNIQUE_ID_BYTES];
+    int64_t rows1[1] = {0};
+    memset(id, 0, sizeof id);
+    CHECK(mgn_dp_unique_id(NULL) == MGN_ERR_INVALID);
+    CHECK(mgn_dp_init(id, 2, 2, &comm) == MGN_ERR_INVALID); /* rank outside [0, world) */
+    CHECK(comm == NULL);
+    CHECK(mgn_dp_init(NULL, 0, 1, &comm) == MGN_ERR_INVALID);
+    CHECK(mgn_dp_allreduce(NULL, NULL, 0, MGN_DP_SUM, NULL) == MGN_ERR_INVALID);
+    CHECK(mgn_dp_allreduce_normaliser(NULL, NULL, NULL, 0, NULL) == MGN_ERR_INVALID);
+    CHECK(mgn_halo_exchange(NULL, NULL, rows1, NULL, rows1, 256, NULL) == MGN_ERR_INVALID);
+    CHECK(mgn_dp_rank(NULL, NULL, NULL) == MGN_ERR_INVALID);
+    CHECK(mgn_backward_dp(NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, 0, NULL, NULL, 4, NULL) == MGN_ERR_INVALID);
+    CHECK(mgn_last_error(msg, sizeof msg) == MGN_OK && strlen(msg) > 0);
+    CHECK(mgn_dp_finalize(NULL) == MGN_OK);
+    CHECK(mgn_library_release() == MGN_OK);
+  }
   printf(failures ? "abi_kat: %d check(s) FAILED\n" : "abi_kat: all checks passed\n", failures);
   return failures ? 1 : 0;
 }

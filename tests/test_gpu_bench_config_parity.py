@@ -1,0 +1,144 @@
+"""Parity of the BENCHMARKED configuration in the BENCHMARKED arithmetic: the tensor-core mode
+(MGN_COMPUTE_BF16) at the full depth of BASELINE configs[1] - 65 x 29 CylinderFlow mesh (N = 1885, E = 10936), latent
+128, 15 message-passing steps - gradient included, against the fp64 oracle; the block-diagonal multi-window graph that
+bench.py times, built exactly as bench.py builds it; and the 32-window bench graph through a size-independent property.
+
+Tolerances ("bf16 mode at 15 MP steps"); the CPU model of the same arithmetic
+(oracle/mgn_oracle_bf16.py) predicts loss 4.3e-3, output 7.0e-3, gradient 1.65e-2, worst tensor 4.9e-2, d/d nf 0.19:
+    loss 1.5e-2 | output 2e-2 | flat gradient 4e-2 | every parameter tensor 0.10 (+1e-3 of the whole gradient's norm)
+    d/d node features 0.30: the input Jacobian of a 15-step ReLU network is discontinuous in the forward point (gate
+    flips), so it is set by WHERE the forward lands, not by the VJP arithmetic (tests/test_oracle_bf16.py pins that).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import mgn_oracle as orc
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL_LOSS, TOL_OUT, TOL_GRAD, TOL_TENSOR, TOL_DNF = 1.5e-2, 2e-2, 4e-2, 0.10, 0.30
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _check_step(pkg, cfg, ps, nf, ef, s, r, tgt, mask, label, want_dnf=True):
+    g_o, loss_o, out_o, dnf_o = orc.step(cfg, ps.astype(np.float64), nf, ef, s, r, tgt, mask, dtype=np.float64)
+    model = pkg.Model(cfg.node_in, cfg.edge_in, cfg.out_dim, cfg.mps, 128, cfg.hidden_layers,
+                      compute_mode=pkg.COMPUTE_BF16)
+    graph = pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r))
+    mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
+    (gs,), loss = pkg.step_(mgn, graph, dev(tgt), dev(mask))
+    out = model.forward(graph, dev(ps), training=True)
+    g = gs.cpu().numpy()
+    e_loss = abs(float(loss.cpu()) - loss_o) / abs(loss_o)
+    e_out, e_g = rel(out.cpu().numpy(), out_o), rel(g, g_o)
+    worst = (0.0, "")
+    for name, off, rows, cols in model.param_layout():
+        ref, got = g_o[off:off + rows * cols], g[off:off + rows * cols]
+        excess = np.linalg.norm(got - ref) - 1e-3 * np.linalg.norm(g_o)
+        worst = max(worst, (excess / max(np.linalg.norm(ref), 1e-30), name))
+    line = f"[{label}] loss {e_loss:.2e} out {e_out:.2e} grad {e_g:.2e} worst tensor {worst[0]:.2e} ({worst[1]})"
+    e_dnf = None
+    if want_dnf:
+        _, dout_o = orc.loss_and_dout(out_o, tgt.astype(np.float64), mask)
+        _, dnf = model.backward(graph, dev(ps), dev(dout_o.astype(np.float32)), want_dnf=True)
+        e_dnf = rel(dnf.cpu().numpy(), dnf_o)
+        line += f" dnf {e_dnf:.2e}"
+    print(line)
+    assert e_loss < TOL_LOSS and e_out < TOL_OUT and e_g < TOL_GRAD, line
+    assert worst[0] < TOL_TENSOR, line
+    if want_dnf:
+        assert e_dnf < TOL_DNF, line
+    return g, float(loss.cpu())
+
+
+def _random_problem(B, seed=0):
+    rng = np.random.default_rng(seed)
+    pos, cells, nt = orc.cylinder_flow_mesh(65, 29)
+    N0 = pos.shape[0]
+    cells = np.concatenate([cells + b * N0 for b in range(B)], axis=0)   # bench.py:71-73
+    nt = np.tile(nt, B)
+    s, r = orc.shift_to_one_based(*orc.triangles_to_edges(cells))
+    N, E = N0 * B, s.shape[0]
+    cfg = orc.ModelConfig(9, 3, 2, 128, 15, 2)
+    ps = (orc.init_params(cfg, seed=seed + 1, dtype=np.float64)
+          + 0.02 * rng.normal(size=orc.mlp_specs(cfg)[1])).astype(np.float32)
+    nf = rng.normal(size=(N, 9)).astype(np.float32)
+    ef = rng.normal(size=(E, 3)).astype(np.float32)
+    tgt = rng.normal(size=(N, 2)).astype(np.float32)
+    return cfg, ps, nf, ef, s, r, tgt, orc.node_mask(nt, [0, 5])
+
+
+def test_bf16_step_full_depth_single_window(pkg):
+    """BASELINE configs[1], one window: loss, output, flat gradient, every parameter tensor and d/d nf at 15 MP steps."""
+    _check_step(pkg, *_random_problem(1), label="65x29, 15 MP steps, 1 window")
+
+
+def test_bf16_step_full_depth_four_window_block_diagonal(pkg):
+    """Four time windows of one trajectory as ONE block-diagonal graph, assembled as bench.py assembles its batch
+    (cells shifted by b*N, node types tiled): 7540 nodes, 43744 edges = 342 edge tiles > 148 SMs, so every CTA of the
+    backward kernels accumulates several tiles' weight gradients in TMEM."""
+    _check_step(pkg, *_random_problem(4, seed=3), label="65x29, 15 MP steps, 4 windows", want_dnf=False)
+
+
+def test_bench_workload_through_the_public_api(pkg):
+    """bench.py's own step (make_workload -> create_base_graph -> init_train_step -> train_step) for 2 windows, in
+    bf16 mode, against the oracle fed with the features the product built: same tolerances."""
+    sys.path.insert(0, ROOT)
+    import bench
+    B = 2
+    data_h, vel, nt, N0 = bench.make_workload(B)
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0)
+    model, ps, st = pkg.build_model(2 + 7, 2, 2, bench.MPS, bench.LATENT, bench.HIDDEN, compute_mode=pkg.COMPUTE_BF16)
+    mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOnline(3),
+                           {"velocity": pkg.NormaliserOnline(2), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
+                           {"velocity": pkg.NormaliserOnline(2)})
+    mask_h = pkg.node_mask(data_h["node_type"].reshape(-1), [0, 5])
+    cur, nxt = bench.sample_frames(vel, 0, B)
+    data = {"velocity": dev(cur)[None], "target|velocity": dev(nxt)[None]}
+    meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}}, "target_features": ["velocity"]}
+    strat = pkg.DerivativeTraining()
+    t = pkg.init_train_step(strat, (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders, receivers, 1,
+                                    dev(mask_h), None))
+    (gs,), loss = pkg.train_step(strat, t)
+    _, graph, target, _ = t
+    cfg = orc.ModelConfig(9, 3, 2, 128, bench.MPS, bench.HIDDEN)
+    g_o, loss_o, _, _ = orc.step(cfg, ps.cpu().numpy().astype(np.float64), graph.node_features.cpu().numpy(),
+                                 graph.edge_features.cpu().numpy(), senders.cpu().numpy(), receivers.cpu().numpy(),
+                                 target.cpu().numpy(), mask_h, dtype=np.float64)
+    e_loss, e_g = abs(float(loss.cpu()) - loss_o) / abs(loss_o), rel(gs.cpu().numpy(), g_o)
+    print(f"[bench step, 2 windows] loss {e_loss:.2e} grad {e_g:.2e}")
+    assert e_loss < TOL_LOSS and e_g < TOL_GRAD
+
+
+def test_32_window_bench_graph_equals_one_window(pkg):
+    """The graph bench.py times by default (32 windows: N = 60320, E = 349952) is beyond what the oracle finishes in
+    seconds; size-independent property instead: 32 IDENTICAL windows give the loss of one window and (mean over masked
+    nodes) the gradient of one window - only the fp32 summation order of the weight-gradient partials differs."""
+    cfg, ps, nf, ef, s, r, tgt, mask = _random_problem(1, seed=5)
+    B = 32
+    N0, E0 = nf.shape[0], s.shape[0]
+    model = pkg.Model(9, 3, 2, 15, 128, 2, compute_mode=pkg.COMPUTE_BF16)
+    mgn = pkg.GraphNetwork(model, dev(ps), None, None, None, None)
+    (g1,), l1 = pkg.step_(mgn, pkg.FeatureGraph(dev(nf), dev(ef), dev(s), dev(r)), dev(tgt), dev(mask))
+    g1, l1 = g1.clone(), float(l1.cpu())
+    sB = np.concatenate([s + b * N0 for b in range(B)]).astype(np.int32)
+    rB = np.concatenate([r + b * N0 for b in range(B)]).astype(np.int32)
+    maskB = np.concatenate([mask + b * N0 for b in range(B)]).astype(np.int32)
+    graph = pkg.FeatureGraph(dev(np.tile(nf, (B, 1))), dev(np.tile(ef, (B, 1))), dev(sB), dev(rB))
+    (gB,), lB = pkg.step_(mgn, graph, dev(np.tile(tgt, (B, 1))), dev(maskB))
+    e_l, e_g = abs(float(lB.cpu()) - l1) / abs(l1), rel(gB.cpu().numpy(), g1.cpu().numpy())
+    print(f"[32 identical windows vs 1] loss {e_l:.2e} grad {e_g:.2e}")
+    assert e_l < 1e-5 and e_g < 2e-3

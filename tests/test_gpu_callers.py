@@ -172,3 +172,35 @@ def test_captured_rollout_replays_the_eager_rollout(pkg, solver):
     sol2_g, _ = cap.replay(x1)
     assert all(torch.equal(a, b) for a, b in zip(sol2, sol2_g))
     assert not torch.equal(sol2_g[-1], sol[-1])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n_buckets", [1, 4, 64])
+def test_backward_dp_single_gpu_equals_step_then_adam(pkg, mode, n_buckets):
+    """SURVEY 8f row 1 / src/MeshGraphNets.jl:374-378: mgn_backward_dp without a communicator = backward with the Adam
+    update of every finished gradient bucket running on a side stream beside the rest of the backward pass.  The same
+    kernels on the same values: gradient, parameters and moments are BITWISE those of step! followed by the update."""
+    data_h, data, meta, mgn, (node_type, senders, receivers, ef), o = _setup(pkg, mode=mode)
+    mask = dev(orc.node_mask(o["nt"], [0, 5]))
+    strat = pkg.DerivativeTraining()
+    t = pkg.init_train_step(strat, (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders, receivers, 1,
+                                    mask, None))
+    _, graph, target, _ = t
+    ps0 = mgn.ps.clone()
+    opt = pkg.Adam(1e-3)
+    st_a, st_b = opt.setup(mgn.ps), opt.setup(mgn.ps)
+    losses = []
+    for _ in range(2):                                  # two steps: the device-side step counter must advance once per step
+        (g_a,), loss_a = pkg.step_(mgn, graph, target, mask)
+        g_a = g_a.clone()
+        opt.update(st_a, mgn.ps, g_a)
+        losses.append(float(loss_a.cpu()))
+    ps_a, mgn.ps = mgn.ps.clone(), ps0.clone()
+    for i in range(2):
+        (g_b,), loss_b = pkg.step_dp_(mgn, graph, target, mask, opt=opt, opt_state=st_b, comm=None, n_buckets=n_buckets)
+        torch.cuda.synchronize()
+        assert float(loss_b.cpu()) == losses[i]
+    assert torch.equal(g_b, g_a)
+    assert torch.equal(mgn.ps, ps_a)
+    assert torch.equal(st_a["m"], st_b["m"]) and torch.equal(st_a["v"], st_b["v"])
+    assert int(st_b["dev"][0].cpu()) == 2
