@@ -55,6 +55,13 @@ def parse():
                     help="time windows (graphs) per step per GPU; the reference is batch 1 (reported as `batch1`)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--dp", default="fused", choices=["fused", "plain"],
+                    help="fused: mgn_backward_dp (bucketed NCCL all-reduce + Adam on a side stream, overlapped with the "
+                         "backward pass, library transport); plain: one torch.distributed all-reduce after backward")
+    ap.add_argument("--buckets", type=int, default=6)
+    ap.add_argument("--no-partition-leg", action="store_true",
+                    help="N > 1: skip the graph-partitioned (BASELINE configs[4]) extra measurement")
+    ap.add_argument("--partition-edges-per-rank", type=float, default=3.4e6)
     return ap.parse_args()
 
 
@@ -238,17 +245,40 @@ def measure(args, rank, world, local_rank, B, steps, warmup, extras):
     loss_buf = torch.zeros(1, device=dev)
     h_loss = torch.zeros(1).pin_memory()
     distributed = world > 1
+    comm = None
     if distributed:
         import torch.distributed as dist
+        comm = extras if isinstance(extras, pkg.Communicator) else None
+    # online-normaliser statistics of all three normalisers in ONE flat buffer: every rank accumulates its own windows,
+    # then new = prev + sum_r (state_r - prev) ("online-normaliser stats must be summed across ranks too")
+    norms = [mgn.e_norm, mgn.n_norm["velocity"], mgn.o_norm["velocity"]]
+    norm_flat = pkg.pack_normaliser_states(norms)
+    norm_prev = torch.empty_like(norm_flat)
+    fused = args.dp == "fused"
 
     def step_body(collective=True):
+        sync = distributed and collective
+        if sync:
+            norm_prev.copy_(norm_flat)                  # the common statistics before this step's accumulation
         t = pkg.init_train_step(strat, (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders,
                                         receivers, 1, mask, None))
-        gs, loss = pkg.train_step(strat, t)
-        for g in gs:
-            if distributed and collective:
-                pkg.allreduce_mean_(g, world)      # one NCCL all-reduce of the flat fp32 gradient
-            opt.update(opt_state, mgn.ps, g)
+        if fused:
+            # forward + loss + backward whose finished gradient buckets are all-reduced (mean) and fed to Adam on a
+            # side stream while the rest of the backward pass runs (mgn_backward_dp)
+            _, graph, target, _ = t
+            gs, loss = pkg.step_dp_(mgn, graph, target, mask, opt=opt, opt_state=opt_state,
+                                    comm=comm if sync else None, n_buckets=args.buckets)
+        else:
+            gs, loss = pkg.train_step(strat, t)
+            for g in gs:
+                if sync:
+                    pkg.allreduce_mean_(g, world)      # one NCCL all-reduce of the flat fp32 gradient
+                opt.update(opt_state, mgn.ps, g)
+        if sync:                                         # new = prev + sum over ranks of (state_r - prev): one collective
+            if comm is not None:
+                comm.allreduce_normaliser_(norm_flat, norm_prev)
+            else:
+                pkg.allreduce_normaliser_(norm_flat, norm_prev)
         loss_buf.copy_(loss)
 
     # ---- optional CUDA graph of the step (all library calls only enqueue on the current stream)
@@ -332,6 +362,10 @@ def measure(args, rank, world, local_rank, B, steps, warmup, extras):
         "config": {"workload": "cylinder_flow_train_step", "nodes": NX * NY, "edges": E // B, "latent": LATENT,
                    "mps": MPS, "hidden_layers": HIDDEN, "graphs_per_step_per_gpu": B, "parallelism": f"dp{world}",
                    "compute_mode": args.mode, "cuda_graph": graph is not None,
+                   "dp": (f"mgn_backward_dp: {args.buckets} gradient buckets, NCCL avg + Adam per bucket on a side stream, "
+                          "overlapped with the backward pass; normaliser statistics merged across ranks every step"
+                          if fused else "one all-reduce after backward, then Adam") if world > 1 else
+                         ("mgn_backward_dp: Adam per gradient bucket on a side stream" if fused else "step! then Adam"),
                    "l2": "flushed between timed steps (256 MB write); per-step CUDA events, max over ranks"},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "clocks": clocks, "final_loss": final_loss,
@@ -346,16 +380,107 @@ def measure(args, rank, world, local_rank, B, steps, warmup, extras):
 
 
 def run_ours(args, rank, world, local_rank):
-    line = measure(args, rank, world, local_rank, args.batch, args.steps, args.warmup, True)
+    import mgn_pkg
+    pkg = mgn_pkg.pkg
+    extras = True
+    if world > 1 and args.dp == "fused":
+        torch.cuda.set_device(local_rank)
+        extras = pkg.Communicator.from_torch_distributed(torch.device("cuda", local_rank))   # the library's own NCCL comm
+    line = measure(args, rank, world, local_rank, args.batch, args.steps, args.warmup, extras)
+    if world > 1 and not args.no_partition_leg:
+        try:
+            leg = partition_leg(args, pkg, rank, world, local_rank, extras if isinstance(extras, pkg.Communicator) else None)
+        except Exception as e:       # never lose the main line
+            leg = {"error": repr(e)}
+        if line is not None:
+            line["partitioned_mesh"] = leg
     if world == 1 and args.batch != 1:
         # the reference's own granularity: ONE window per step (batchsize is "not implemented yet",
         # src/MeshGraphNets.jl:224) - a latency number, reported beside the throughput headline
         b1 = measure(args, rank, world, local_rank, 1, min(args.steps, 20), max(3, min(args.warmup, 5)), False)
         if line is not None and b1 is not None:
+            from bench_roofline import peaks, survey_flops
+            pk = peaks()
+            tf = survey_flops(10936, NX * NY, LATENT, HIDDEN + 2, MPS, 9, 3, 2) * 3 / (b1["ms_per_step"] * 1e-3) / 1e12
             line["batch1"] = {"ms_per_step": b1["ms_per_step"], "value": b1["value"], "unit": UNIT,
-                              "train_steps_per_sec": b1["train_steps_per_sec"], "e2e_ms_per_step": b1["e2e"]["ms_per_step"]}
+                              "train_steps_per_sec": b1["train_steps_per_sec"], "e2e_ms_per_step": b1["e2e"]["ms_per_step"],
+                              "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_tflops_sustained"],
+                                           "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops_sustained"],
+                                           "note": "one window = 86 edge tiles < 148 SMs and a 7 MB working set in L2: "
+                                                   "launch / latency bound; algorithmic FLOPs of SURVEY 8d (3 x forward) "
+                                                   "against the sustained bf16 peak (84 us per step at peak)"}}
     if line is not None:
         emit(line)
+
+
+def partition_leg(args, pkg, rank, world, local_rank, comm):
+    """BASELINE configs[4] on the driver's record: one training step of a Kuhn tetrahedral grid partitioned over the
+    ranks (about --partition-edges-per-rank edges each; 126^3 nodes / 27.6 M edges at N = 8), halo rows exchanged
+    every message-passing step through mgn_halo_exchange (grouped NCCL send/recv on the compute stream), the parameter
+    gradient summed with mgn_dp_allreduce.  Device-timed, max over ranks; exchange time = sum of CUDA-event pairs
+    around the exchanges of rank 0's stream inside the same steps."""
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    n = max(8, int(round((args.partition_edges_per_rank * world / 13.8) ** (1.0 / 3.0))))
+    N = n ** 3
+    s, r = pkg.parse_edges(pkg.tet_grid_edges(n))
+    E = int(s.shape[0])
+    part = pkg.build_partition_rank(N, s, r, world, rank)
+    del s, r
+    rng = np.random.default_rng(1234 + rank)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    nf = to(rng.normal(size=(part.n_local, 4)).astype(np.float32))
+    ef = to(rng.normal(size=(len(part.edge_ids), 4)).astype(np.float32))
+    tgt = to(rng.normal(size=(part.n_local, 3)).astype(np.float32))
+    mask = to(np.arange(1, part.n_own + 1, dtype=np.int32))
+    mode = pkg.COMPUTE_BF16 if args.mode == "bf16" else pkg.COMPUTE_FP32
+    model, ps, _ = pkg.build_model(4, 3, 3, MPS, LATENT, HIDDEN, device=dev, compute_mode=mode)
+    pm = pkg.PartitionedModel(model, part, nf, ef, device=dev)
+    base = pkg.AbiExchange(part, world, comm, model) if comm is not None else pkg.DistExchange(part, world, dev, model)
+    ev = []
+
+    def timed_exchange(sends, direction):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = base(sends, direction)
+        b.record()
+        ev.append((a, b))
+        return out
+
+    def step(ex):
+        grads, losses, _ = pkg.run_partitioned_step([pm], ps, [tgt], [mask], N, ex, pkg.masked_mse_partial)
+        if comm is not None:
+            comm.allreduce_sum_(grads[0]); comm.allreduce_sum_(losses[0])
+        else:
+            dist.all_reduce(grads[0]); dist.all_reduce(losses[0])
+        return losses[0]
+
+    step(base)
+    torch.cuda.synchronize()
+    dist.barrier()
+    K = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        loss = step(timed_exchange)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    ex_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    halo = sum(len(v) for v in part.recv_rows.values())
+    tt = torch.tensor([ms, ex_ms, float(halo), float(len(part.edge_ids))], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ws_gb = model.workspace_bytes(pm.graph.index, True) / 1e9
+    lat_b, grad_b = model.halo_row_bytes(pkg.HALO_LATENT), model.halo_row_bytes(pkg.HALO_GRAD)
+    return {"workload": f"kuhn_tet_grid_{n}^3_partitioned_train_step", "nodes": N, "edges": E, "mps": MPS,
+            "ms_per_step": float(tt[0]), "mp_step_edges_per_sec": E * MPS / (float(tt[0]) * 1e-3),
+            "exchange_ms_per_step_max_rank": float(tt[1]), "exchanges_per_step": 2 * MPS - 1,
+            "halo_rows_max_rank": int(tt[2]), "edges_max_rank": int(tt[3]),
+            "halo_bytes_per_step_max_rank": int(tt[2]) * ((MPS - 1) * lat_b + MPS * grad_b),
+            "workspace_gb_rank0": ws_gb, "steps": K,
+            "transport": "mgn_halo_exchange (library NCCL, grouped send/recv on the compute stream)" if comm is not None
+                         else "torch.distributed all_to_all_single",
+            "final_loss": float(loss.cpu())}
 
 
 def extra_measurements(args, pkg, model, mgn, E, B, dev, step_fn, n_nodes):

@@ -64,6 +64,27 @@ def algorithmic_work(E, N, D, L, mps, node_in, edge_in, out_dim):
             "tc_dw": (i_flops, i_bytes)}
 
 
+def survey_flops(E, N, D, L, mps, node_in, edge_in, out_dim):
+    """Algorithmic FLOPs of ONE full forward; a training step is 3x (no-recompute convention)."""
+    D2 = D * D
+    return (mps * 2 * D2 * ((L + 2) * E + (L + 1) * N)
+            + 2 * ((node_in * D + (L - 1) * D2) * N + (edge_in * D + (L - 1) * D2) * E)
+            + 2 * ((L - 1) * D2 + D * out_dim) * N)
+
+
+def survey_forward_bytes(E, N, D, L, mps, node_in, edge_in, out_dim, s):
+    """Algorithmic bytes of the fused-forward launches of ONE training step exactly as SURVEY.md 8(d) counts them,
+    s = bytes per STORED latent element (4: the fp32 master latents this library keeps): per MP step
+    2 E D s (ef read + write) + 3 N D s (nf gather source once, nf read + write) + 8 E + 4 (N + 1) (indices) +
+    (2L + 3) D^2 weight elements once per launch (bf16 images); encoders read the raw features and write the latents,
+    the decoder reads the node latent and writes the output.  Saved activations are NOT counted here (8d lets the
+    builder state them: they are the difference between `frac_alg` and `frac_design`)."""
+    per_step = 2 * E * D * s + 3 * N * D * s + 8 * E + 4 * (N + 1) + (2 * L + 3) * D * D * 2
+    enc = (4 * node_in + D * s) * N + (4 * edge_in + D * s + 4) * E + 2 * ((node_in + edge_in) * D + 2 * (L - 1) * D * D)
+    dec = D * s * N + 4 * out_dim * N + 2 * ((L - 1) * D * D + D * out_dim)
+    return mps * per_step + enc + dec
+
+
 def ncu_traffic():
     """Per-launch DRAM traffic of the kernels from the committed `ncu --set full` capture, if any."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -112,6 +133,16 @@ def roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn=None, n_node
             gbs = nbytes / sec / 1e9
             row.update({"gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"], "alg_bytes_per_launch": nbytes / launches,
                         "alg_flops_per_launch": flops / launches})
+            if name == "tc_mlp_fwd":    # SURVEY 8(d) bytes (fp32 stored latents), without the saved activations
+                alg = survey_forward_bytes(E, n_nodes, D, L, MPS, 9, 3, 2, 4)
+                row.update({"survey8d_bytes_per_step": alg, "frac_alg": alg / sec / 1e9 / pk["hbm_gbs"],
+                            "frac_design": gbs / pk["hbm_gbs"]})
+            t = traffic.get(name)
+            if t:
+                row["dram_bytes_per_launch_ncu"] = t
+                row["traffic_ratio_vs_design"] = t * launches / nbytes
+                if name == "tc_mlp_fwd":
+                    row["traffic_ratio"] = t * launches / row["survey8d_bytes_per_step"]
         rows.append(row)
     if not rows:
         return out
@@ -121,11 +152,17 @@ def roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn=None, n_node
     if "gbs" in top and top["hbm_frac"] >= top["tensor_frac"]:
         out["roofline"] = {"kernel": top["kernel"], "bound": "hbm", "achieved": top["gbs"], "peak": pk["hbm_gbs"],
                            "unit": "GB/s", "frac": top["hbm_frac"],
+                           "frac_design": top["hbm_frac"], "frac_alg": top.get("frac_alg"),
+                           "traffic_ratio": top.get("traffic_ratio", top.get("traffic_ratio_vs_design")),
                            "traffic": traffic.get(top["kernel"]), "launches_timed": top["launches_per_step"] * reps,
                            "avg_launch_us": top["avg_launch_us"], "tensor_frac": top["tensor_frac"],
-                           "note": f"dominant kernel family by time inside the step; algorithmic bytes per DESIGN.md "
-                                   f"section 3 / launch duration by CUDA events; peak = {pk['source']} HBM copy "
-                                   f"bandwidth; tensor_frac is against the {pk['source']} sustained bf16 peak"}
+                           "note": f"dominant kernel family by time inside the step; frac = frac_design: every byte the "
+                                   f"launch must move once in THIS design (DESIGN.md section 3: fp32 masters + saved "
+                                   f"activations) / launch duration by CUDA events; frac_alg (forward family only): "
+                                   f"SURVEY 8(d) bytes at s = 4 without saved activations; traffic = ncu DRAM bytes "
+                                   f"per launch (profiles/ncu_traffic.json), traffic_ratio = traffic / algorithmic; "
+                                   f"peak = {pk['source']} HBM copy bandwidth; tensor_frac is against the "
+                                   f"{pk['source']} sustained bf16 peak"}
     else:
         out["roofline"] = {"kernel": top["kernel"], "bound": "tensor", "achieved": top["tflops"],
                            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": top["tensor_frac"],

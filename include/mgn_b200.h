@@ -99,6 +99,22 @@ int32_t mgn_edge_features(const float* h_pos, int64_t n_nodes, int32_t dim, cons
                           const int32_t* h_receivers, int64_t n_edges, int32_t index_base,
                           float* h_out);
 
+/* ------------------------------------------------------------------ create_base_graph on the device */
+/* The same five operations with inputs and outputs resident in HBM (src/graph.jl:25-55 when the trajectory already
+ * lives on the device): bit-exact equal to the host functions above.  Graph construction, like mgn_graph_create, may
+ * allocate scratch and synchronise `stream` (to hand E / the shift flag back to the host); it is not for capture. */
+int32_t mgn_one_hot_device(const int32_t* d_v, int64_t n, int32_t depth, int32_t offset, float* d_out, void* stream);
+/* d_senders / d_receivers need room for 6*C entries; *h_n_edges receives E. */
+int32_t mgn_triangles_to_edges_device(const int32_t* d_cells, int64_t n_cells, int32_t* d_senders,
+                                      int32_t* d_receivers, int64_t* h_n_edges, void* stream);
+int32_t mgn_parse_edges_device(const int32_t* d_edges, int64_t n_pairs, int32_t* d_senders, int32_t* d_receivers,
+                               void* stream);
+int32_t mgn_shift_one_based_device(int32_t* d_senders, int32_t* d_receivers, int64_t n_edges, int32_t* h_shifted,
+                                   void* stream);
+int32_t mgn_edge_features_device(const float* d_pos, int64_t n_nodes, int32_t dim, const int32_t* d_senders,
+                                 const int32_t* d_receivers, int64_t n_edges, int32_t index_base, float* d_out,
+                                 void* stream);
+
 /* ------------------------------------------------------------------ graph handle (device CSR; NEW) */
 /* Builds, on the device, the stable sort of edge ids by receiver (CSR) and by sender (CSC) that
  * turns GraphNetCore's NNlib.scatter(+) into an atomics-free segmented sum.  d_senders /

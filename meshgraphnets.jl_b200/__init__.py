@@ -16,8 +16,8 @@ from .core import (Adam, FeatureGraph, step_dp_, GraphIndex, GraphNetwork, Model
                    inverse_data, mse_reduce, one_hot, parse_edges, profile_begin, profile_end, profile_tag,
                    shift_one_based, step_,
                    triangles_to_edges)
-from .graph import build_graph, create_base_graph  # noqa: F401
-from .parallel import Communicator, allreduce_mean_, allreduce_normaliser_, allreduce_sum_, shard_windows  # noqa: F401
+from .graph import build_graph, create_base_graph, create_base_graph_device  # noqa: F401
+from .parallel import Communicator, pack_normaliser_states, allreduce_mean_, allreduce_normaliser_, allreduce_sum_, shard_windows  # noqa: F401
 from .partition import (AbiExchange, DistExchange, LocalExchange, LocalGraph, PartitionedModel, build_partition,  # noqa: F401
                         build_partition_rank,
                         masked_mse_partial, partition_bounds, run_partitioned_step)

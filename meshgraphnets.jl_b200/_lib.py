@@ -57,6 +57,11 @@ SIGNATURES = {
     "mgn_parse_edges": [_p, _i64, _p, _p],
     "mgn_shift_one_based": [_p, _p, _i64, C.POINTER(_i32)],
     "mgn_edge_features": [_p, _i64, _i32, _p, _p, _i64, _i32, _p],
+    "mgn_one_hot_device": [_p, _i64, _i32, _i32, _p, _p],
+    "mgn_triangles_to_edges_device": [_p, _i64, _p, _p, C.POINTER(_i64), _p],
+    "mgn_parse_edges_device": [_p, _i64, _p, _p, _p],
+    "mgn_shift_one_based_device": [_p, _p, _i64, C.POINTER(_i32), _p],
+    "mgn_edge_features_device": [_p, _i64, _i32, _p, _p, _i64, _i32, _p, _p],
     "mgn_graph_create": [_i64, _i64, _p, _p, _i32, _p, C.POINTER(_p)],
     "mgn_graph_destroy": [_p],
     "mgn_graph_sizes": [_p, C.POINTER(_i64), C.POINTER(_i64)],

@@ -50,6 +50,18 @@ def allreduce_normaliser_(state: torch.Tensor, prev: torch.Tensor):
     return state
 
 
+def pack_normaliser_states(norms):
+    """Moves the device state of several NormaliserOnline objects into ONE flat buffer (each `.state` becomes a view of
+    it), so that their data-parallel merge is a single all-reduce."""
+    flat = torch.cat([n.state.reshape(-1) for n in norms])
+    off = 0
+    for n in norms:
+        k = n.state.numel()
+        n.state = flat[off:off + k]
+        off += k
+    return flat
+
+
 class Communicator:
     """mgn_comm handle: the library's own NCCL transport (mgn_dp_* of include/mgn_b200.h) - what a Julia caller has,
     since it cannot use torch.distributed.  The 128-byte NCCL id is created by rank 0 (mgn_dp_unique_id) and handed to

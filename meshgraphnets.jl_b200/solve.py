@@ -92,7 +92,8 @@ def _step_plan(start, stop, dt, saves):
     (src/solve.jl:62): the integrator advances in steps of ``dt`` from ``start`` and a save time must coincide with a
     grid point (interpolated saves are OrdinaryDiffEq's dense output: out of scope, so they raise instead of silently
     landing on the wrong physical time).  ``dt = None`` is the ``tstops = saves`` branch (:60): one step per save
-    interval.  Returns [(n_sub, h)] per save interval, preceded by the (start -> saves[0]) lead-in."""
+    interval.  Returns [(n_sub, h, t0)] per save interval (t0 = the Float32 time the interval starts at: sub-step j
+    runs at Float32(t0 + j*h), never at an accumulated sum), preceded by the (start -> saves[0]) lead-in."""
     saves = [float(np.float32(v)) for v in saves]
     if len(saves) < 2:
         raise MgnError(-1, "rollout needs at least two save times (saves[2] - saves[1] is the inflow data spacing)")
@@ -105,22 +106,20 @@ def _step_plan(start, stop, dt, saves):
         if span < -1e-9:
             raise MgnError(-1, "save times must be increasing")
         if dt is None:
-            plan.append((1 if span > 1e-9 * max(1.0, abs(b)) else 0, np.float32(span)))
+            plan.append((1 if span > 1e-9 * max(1.0, abs(b)) else 0, np.float32(span), np.float32(a)))
             continue
         n = int(round(span / float(dt)))
         if abs(n * float(dt) - span) > 1e-4 * float(dt) + 1e-7 * max(1.0, abs(b)):
             raise MgnError(-1, f"the fixed step dt = {dt} does not divide the save interval ({a}, {b}): saves between "
                                "grid points need dense output, which this mirror does not provide")
-        plan.append((n, np.float32(dt)))
+        plan.append((n, np.float32(dt), np.float32(a)))
     return start, saves, plan
 
 
 def _integrate(f, x, start, plan, solver, on_save):
-    t = np.float32(start)
-    for k, (n_sub, h) in enumerate(plan):
-        for _ in range(n_sub):
-            x = rk_step(f, x, t, h, solver)
-            t = np.float32(t + h)
+    for k, (n_sub, h, t0) in enumerate(plan):
+        for j in range(n_sub):
+            x = rk_step(f, x, np.float32(t0 + np.float32(j) * h), h, solver)
         on_save(k, x)
     return x
 
@@ -156,7 +155,7 @@ class CapturedRollout:
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         start, saves_f, plan = _step_plan(start, stop, dt, saves)
-        h0 = next((h for n, h in plan if n > 0), np.float32(saves[1] - saves[0]))
+        h0 = next((h for n, h, _ in plan if n > 0), np.float32(saves[1] - saves[0]))
         with torch.cuda.stream(side):             # warm-up: allocations and first-use scratch happen outside capture
             for _ in range(2):
                 rk_step(lambda xx, tt: ode_func_eval(xx, p, tt), self.x0.clone(), np.float32(start), h0, solver)

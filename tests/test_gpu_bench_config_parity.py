@@ -141,4 +141,4 @@ def test_32_window_bench_graph_equals_one_window(pkg):
     (gB,), lB = pkg.step_(mgn, graph, dev(np.tile(tgt, (B, 1))), dev(maskB))
     e_l, e_g = abs(float(lB.cpu()) - l1) / abs(l1), rel(gB.cpu().numpy(), g1.cpu().numpy())
     print(f"[32 identical windows vs 1] loss {e_l:.2e} grad {e_g:.2e}")
-    assert e_l < 1e-5 and e_g < 2e-3
+    assert e_l < 1e-5 and e_g < 1e-4      # 0 and 1.5e-6 observed

@@ -14,23 +14,24 @@ def test_one_step_per_save_when_dt_equals_the_spacing(pkg):
     start, ts, plan = _plan(pkg)(0.0, 0.5, 0.01, saves)
     assert start == 0.0 and len(ts) == 51 and len(plan) == 51
     assert plan[0][0] == 0                       # saves[0] == start: the initial state is the first save
-    assert all(n == 1 for n, _ in plan[1:]) and all(h == np.float32(0.01) for _, h in plan[1:])
+    assert all(n == 1 for n, _, _ in plan[1:]) and all(h == np.float32(0.01) for _, h, _ in plan[1:])
+    assert [t0 for _, _, t0 in plan[1:]] == [np.float32(v) for v in saves[:-1]]      # interval starts are the save times
 
 
 def test_sub_steps_when_dt_divides_the_spacing(pkg):
     """dt = 0.005 with saves every 0.01: two steps per save (the round-1 mirror took one and mislabelled the time)."""
     start, ts, plan = _plan(pkg)(0.0, 0.1, 0.005, [0.0, 0.01, 0.02, 0.04])
-    assert [n for n, _ in plan] == [0, 2, 2, 4]
+    assert [n for n, _, _ in plan] == [0, 2, 2, 4]
 
 
 def test_lead_in_from_start_to_the_first_save(pkg):
     start, ts, plan = _plan(pkg)(0.0, 0.1, 0.01, [0.02, 0.03])
-    assert [n for n, _ in plan] == [2, 1] and start == 0.0
+    assert [n for n, _, _ in plan] == [2, 1] and start == 0.0
 
 
 def test_dt_none_is_the_tstops_branch(pkg):
     start, ts, plan = _plan(pkg)(0.0, 0.1, None, [0.0, 0.01, 0.03])
-    assert [n for n, _ in plan] == [0, 1, 1]
+    assert [n for n, _, _ in plan] == [0, 1, 1]
     assert abs(float(plan[2][1]) - 0.02) < 1e-7
 
 
