@@ -281,6 +281,54 @@ int32_t mgn_norm_online_apply(const float* d_x, int64_t rows, int32_t features,
 int32_t mgn_affine_apply(const float* d_x, int64_t rows, int32_t features, float scale,
                          float shift, float* d_y, int32_t ld_y, int32_t col_y, void* stream);
 
+/* ------------------------------------------------------------------ build_graph / inverse_data fused into the model */
+/* `build_graph` (src/graph.jl:75-97) is `nf = vcat(n_norm[f](data[f][:, :, t]) for f in fields..., n_norm["node_type"](
+ * onehot))`, `ef = e_norm(edge_features)`; ode_step (src/solve.jl:205-218) post-processes the output with
+ * `inverse_data(o_norm[tf], out[cols]) .* val_mask`.  Instead of materialising those matrices the caller DESCRIBES them:
+ * a list of column blocks, each the image of a raw matrix under an offline (affine) or an online normaliser.  In the
+ * tensor-core mode the first Dense layer of the encoders evaluates the recipe while staging its operand, the decoder's
+ * last epilogue applies the inverse map and the mask, and the backward kernels apply the transposed maps where they
+ * read the features / the cotangent and where they write d_dx; the fp32 mode materialises each recipe with one launch.
+ * Statistics are READ (never accumulated) here: run mgn_norm_online_update_multi first when the step accumulates. */
+enum { MGN_FEAT_AFFINE = 0,   /* y = x * scale + shift   (NormaliserOfflineMinMax / MeanStd; {1, 0} = copy)      */
+       MGN_FEAT_ONLINE = 1 }; /* y = (x - mean) / std from d_state (node / edge blocks); y * std + mean (outputs) */
+typedef struct mgn_feature_seg {
+  const float* d_x;     /* [rows][ld] source matrix (unused for output blocks)                      */
+  int32_t ld, col, width; /* the block is columns [col, col + width) of d_x                          */
+  int32_t kind;         /* MGN_FEAT_*                                                                */
+  float scale, shift;   /* MGN_FEAT_AFFINE (for output blocks: the INVERSE map's scale and shift)    */
+  const float* d_state; /* MGN_FEAT_ONLINE: [sum | sum_sq | count | num_acc], 2 * width + 2 floats   */
+  float std_eps;
+} mgn_feature_seg;
+typedef struct mgn_fused_io {
+  int32_t n_node_segs;  /* blocks of the node-feature matrix in vcat order (src/graph.jl:80-86); widths sum to node_in */
+  mgn_feature_seg node[8];
+  int32_t n_edge_segs;  /* blocks of the edge-feature matrix (src/graph.jl:93), rows in ORIGINAL edge order */
+  mgn_feature_seg edge[8];
+  int32_t n_out_segs;   /* inverse_data per target field (src/solve.jl:205-210); 0 = return the network output */
+  mgn_feature_seg out[8];
+  const float* d_val_mask; /* [N][out_dim] (src/solve.jl:218) or NULL */
+} mgn_fused_io;
+/* mgn_forward with the recipes in place of d_nf / d_ef; d_out = val_mask .* inverse_data(model(...)). */
+int32_t mgn_forward_fused(const mgn_model* m, const mgn_graph* g, const float* d_params, const mgn_fused_io* io,
+                          float* d_out, void* d_workspace, size_t workspace_bytes, int32_t training, void* stream);
+/* Pullback of mgn_forward_fused (what ZygoteVJP derives for ode_step, src/strategies.jl:183-194): d_dout is the
+ * cotangent of the FUSED output; d_dx [N][node_in] (nullable) receives the gradient w.r.t. the RAW source columns of the
+ * node blocks, in vcat order (the transposed normalisers are applied). */
+int32_t mgn_backward_fused(const mgn_model* m, const mgn_graph* g, const float* d_params, const mgn_fused_io* io,
+                           const float* d_dout, float* d_dparams, float* d_dx, void* d_workspace,
+                           size_t workspace_bytes, void* stream);
+/* The accumulate branch of up to 8 online normalisers (every n_norm / e_norm / o_norm call of one step: src/graph.jl:
+ * 80,84,93 and src/strategies.jl:399-410) in TWO launches: x is columns [col, col + features) of a [rows][ld] matrix. */
+typedef struct mgn_norm_update {
+  const float* d_x;
+  int64_t rows;
+  int32_t ld, col, features;
+  float* d_state;
+  float max_acc;
+} mgn_norm_update;
+int32_t mgn_norm_online_update_multi(const mgn_norm_update* h_jobs, int32_t n_jobs, void* stream);
+
 /* ------------------------------------------------------------------ NeuralODE callers (src/solve.jl, SolverStrategy of src/strategies.jl) */
 /* The state of the NeuralODE is x [N][S] (S = sum of the target feature dims; src/strategies.jl:171-172).  A solver
  * strategy evaluates ode_func_train (src/solve.jl:101-115) many times per training step; the pieces of that right-hand

@@ -24,7 +24,8 @@ from .partition import (AbiExchange, DistExchange, LocalExchange, LocalGraph, Pa
 from ._lib import NORM_FORWARD, NORM_FORWARD_VJP, NORM_INVERSE, NORM_INVERSE_VJP  # noqa: F401
 from ._lib import (HALO_GRAD, HALO_LATENT, ROWS_ADD, ROWS_PACK, ROWS_PACK_ZERO, ROWS_UNPACK, STAGE_DECODE,  # noqa: F401
                    STAGE_ENCODE)
-from .solve import CapturedRollout, ode_func_eval, ode_step, rk_step, rollout  # noqa: F401
+from .fused import FusedGraph, backward_fused, forward_fused, update_online  # noqa: F401
+from .solve import CapturedRollout, ode_func_eval, ode_step, ode_step_unfused, rk_step, rollout  # noqa: F401
 from .workloads import (chain_edges, cylinder_flow_mesh, node_mask, synthetic_velocity, tet_grid_edges,  # noqa: F401
                         val_mask)
 from .strategies import (DerivativeTraining, MultipleShooting, SolverTraining, get_delta, init_train_step,  # noqa: F401

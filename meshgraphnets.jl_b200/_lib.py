@@ -17,6 +17,7 @@ HALO_LATENT, HALO_GRAD = 0, 1
 ROWS_PACK, ROWS_UNPACK, ROWS_ADD, ROWS_PACK_ZERO = 0, 1, 2, 3
 NORM_FORWARD, NORM_INVERSE, NORM_FORWARD_VJP, NORM_INVERSE_VJP = 0, 1, 2, 3
 DP_SUM, DP_MEAN = 0, 1
+FEAT_AFFINE, FEAT_ONLINE = 0, 1
 DP_UNIQUE_ID_BYTES = 128
 
 
@@ -38,6 +39,24 @@ class AdamConfig(C.Structure):
     """mgn_adam_config of include/mgn_b200.h (mgn_backward_dp)."""
     _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
                 ("d_m", C.c_void_p), ("d_v", C.c_void_p), ("d_state16", C.c_void_p)]
+
+
+class FeatureSeg(C.Structure):
+    """mgn_feature_seg"""
+    _fields_ = [("d_x", C.c_void_p), ("ld", C.c_int32), ("col", C.c_int32), ("width", C.c_int32), ("kind", C.c_int32),
+                ("scale", C.c_float), ("shift", C.c_float), ("d_state", C.c_void_p), ("std_eps", C.c_float)]
+
+
+class FusedIo(C.Structure):
+    """mgn_fused_io"""
+    _fields_ = [("n_node_segs", C.c_int32), ("node", FeatureSeg * 8), ("n_edge_segs", C.c_int32), ("edge", FeatureSeg * 8),
+                ("n_out_segs", C.c_int32), ("out", FeatureSeg * 8), ("d_val_mask", C.c_void_p)]
+
+
+class NormUpdate(C.Structure):
+    """mgn_norm_update"""
+    _fields_ = [("d_x", C.c_void_p), ("rows", C.c_int64), ("ld", C.c_int32), ("col", C.c_int32), ("features", C.c_int32),
+                ("d_state", C.c_void_p), ("max_acc", C.c_float)]
 
 
 class ParamEntry(C.Structure):
@@ -93,6 +112,9 @@ SIGNATURES = {
     "mgn_affine_apply_ld": [_p, _i32, _i32, _i64, _i32, _f32, _f32, _p, _i32, _i32, _p],
     "mgn_shooting_mse": [_p, _p, _p, _i64, _i64, _f32, _i32, _p, _p, _p],
     "mgn_shooting_continuity": [_p, _p, _i64, _f32, _p, _p, _p],
+    "mgn_forward_fused": [_p, _p, _p, C.POINTER(FusedIo), _p, _p, _sz, _i32, _p],
+    "mgn_backward_fused": [_p, _p, _p, C.POINTER(FusedIo), _p, _p, _p, _p, _sz, _p],
+    "mgn_norm_online_update_multi": [C.POINTER(NormUpdate), _i32, _p],
     "mgn_dp_unique_id": [_p],
     "mgn_dp_init": [_p, _i32, _i32, C.POINTER(_p)],
     "mgn_dp_finalize": [_p],

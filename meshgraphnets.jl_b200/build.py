@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(CSRC, "libmgn_b200.so")
-SOURCES = ["abi.cu", "device_state.cu", "device_graph.cu", "csr.cu", "simt_kernels.cu", "solver_kernels.cu", "pipeline.cu", "dp.cu", "tc_kernels.cu",
+SOURCES = ["abi.cu", "device_state.cu", "device_graph.cu", "features.cu", "csr.cu", "simt_kernels.cu", "solver_kernels.cu", "pipeline.cu", "dp.cu", "tc_kernels.cu",
            "tc_bwd_kernels.cu", "tc_pipeline.cu"]
 # test-only probe of the tcgen05 building blocks: its own library, never linked into the product
 PROBE_LIB = os.path.join(CSRC, "libmgn_b200_probe.so")

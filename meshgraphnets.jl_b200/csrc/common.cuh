@@ -61,7 +61,7 @@ int device_sm_count();  // SMs of the current device (cached per device, thread-
 // partial sums.  Allocated on first use under a mutex; if that first use happens inside a stream capture the
 // allocation is made with the thread's capture mode relaxed, so the capture stays valid.  A captured graph keeps
 // the scratch of its capture stream: replay one graph instance at a time.
-enum ScratchKind : int { SCRATCH_LOSS = 0, SCRATCH_NORM = 1, SCRATCH_KINDS };
+enum ScratchKind : int { SCRATCH_LOSS = 0, SCRATCH_NORM = 1, SCRATCH_NORM_MULTI = 2, SCRATCH_KINDS };
 cudaError_t stream_scratch(cudaStream_t st, int kind, size_t bytes, void** out);
 void release_device_state();  // frees every scratch buffer (mgn_library_release)
 
@@ -233,6 +233,7 @@ int32_t build_graph_index(mgn_graph* g, const int32_t* d_senders, const int32_t*
                           cudaStream_t st);
 
 // ---- orchestration: pipeline.cu --------------------------------------------------------------
+struct FusedIo;  // features.cuh: build_graph / inverse_data recipes evaluated inside the model kernels (nullptr: plain tensors)
 // Notified by the backward pass, on the host, right after the launches that FINISH the gradient of MLP `mi` have been
 // enqueued on the stream; MLPs finish in descending index order (decoder first), so mlp_done(mi) means that the flat
 // gradient range from MLP mi to the end is final on the stream (dp.cu buckets the all-reduce / Adam update on it).
@@ -243,16 +244,17 @@ struct GradHook {
 int32_t workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training, size_t* bytes);
 int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                 const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
-                cudaStream_t st);
+                cudaStream_t st, const FusedIo* io = nullptr);
 int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                  const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                 size_t ws_bytes, cudaStream_t st, GradHook* hook = nullptr);
+                 size_t ws_bytes, cudaStream_t st, GradHook* hook = nullptr, const FusedIo* io = nullptr);
 int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                       const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
-                      cudaStream_t st);
+                      cudaStream_t st, const FusedIo* io = nullptr);
 int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                        const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                       size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook = nullptr);
+                       size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook = nullptr,
+                       const FusedIo* io = nullptr);
 int32_t halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
                   int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st);
 // Row pack / unpack / add between a [N][row_elems] tensor of elem_bytes-wide elements and a contiguous buffer.

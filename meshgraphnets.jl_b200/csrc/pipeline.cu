@@ -13,6 +13,7 @@
 // aggregation is a contiguous segmented sum and the receiver gather is near-sequential.
 #include "common.cuh"
 #include "tc.cuh"
+#include "features.cuh"
 
 namespace mgn {
 namespace {
@@ -40,6 +41,8 @@ struct Workspace {
   std::vector<float*> agg;             // [mps] or [1]
   std::vector<MlpSaved> saved;         // one per MLP (training) or one shared
   float* msg = nullptr;                // [E][D] LayerNorm output of the edge MLP
+  // fused build_graph / inverse_data (mgn_forward_fused): the fp32 mode materialises the recipes with one launch each
+  float *feat_n = nullptr, *feat_e = nullptr, *dout_f = nullptr;
   // backward scratch
   float *dzA = nullptr, *dzB = nullptr, *dxn = nullptr, *dxe = nullptr, *d_nf = nullptr,
         *d_ef = nullptr, *dw_partial = nullptr, *ln_partial = nullptr;
@@ -72,6 +75,9 @@ void layout(const mgn_model* m, const mgn_graph* g, bool training, void* base, W
   w.agg.resize(training ? mps : 1);
   for (auto& a : w.agg) a = b.f((size_t)N * D);
   w.msg = b.f((size_t)E * D);
+  w.feat_n = b.f((size_t)N * m->cfg.node_in);
+  w.feat_e = b.f((size_t)std::max<int64_t>(E, 1) * m->cfg.edge_in);
+  w.dout_f = b.f((size_t)N * m->cfg.out_dim);
   const size_t n_mlps = m->mlps.size();
   w.saved.resize(training ? n_mlps : 1);
   for (size_t i = 0; i < w.saved.size(); ++i) {
@@ -181,9 +187,9 @@ constexpr int kStageAll = -3;   // run every stage (mgn_forward / mgn_backward)
 
 int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                       const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
-                      cudaStream_t st) {
+                      cudaStream_t st, const FusedIo* io) {
   if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
-    return tc_forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, stage, st);
+    return tc_forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, stage, st, io);
   Workspace w;
   layout(m, g, training, ws, w);
   if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_forward");
@@ -195,6 +201,12 @@ int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* param
   const bool all = stage == kStageAll;
 
   if (all || stage == MGN_STAGE_ENCODE) {
+    if (io) {  // normalise + concat (src/graph.jl:75-97) materialised by one launch per entity kind
+      MGN_CUDA_TRY(build_features(io->node, N, w.feat_n, st));
+      MGN_CUDA_TRY(build_features(io->edge, E, w.feat_e, st));
+      nf = w.feat_n;
+      ef = w.feat_e;
+    }
     // Encoder.  Raw edge features arrive in original order: gather through perm.
     MGN_CUDA_TRY(mlp_forward(m->mlps[0], params, op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N,
                              saved(0), eps, w.nf[0], nullptr, nullptr, nullptr, st));
@@ -227,15 +239,17 @@ int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* param
     const size_t di = m->mlps.size() - 1;
     MGN_CUDA_TRY(mlp_forward(m->mlps[di], params, op1(w.nf[lat(mps)], nullptr, D, D), N, saved(di), eps,
                              nullptr, nullptr, nullptr, out, st));
+    if (io && (io->out.n > 0 || io->val_mask))  // inverse_data(...) .* val_mask (src/solve.jl:205-218)
+      MGN_CUDA_TRY(finish_output(io->out, io->val_mask, N, m->cfg.out_dim, out, st));
   }
   return MGN_OK;
 }
 
 int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                        const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                       size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook) {
+                       size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook, const FusedIo* io) {
   if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
-    return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, stage, st, hook);
+    return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, stage, st, hook, io);
   auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi) : MGN_OK; };
   Workspace w;
   layout(m, g, true, ws, w);
@@ -245,7 +259,15 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
   const size_t di = m->mlps.size() - 1;
   const bool all = stage == kStageAll;
 
+  if (io) {  // the features the matching forward materialised
+    nf = w.feat_n;
+    ef = w.feat_e;
+  }
   if (all || stage == MGN_STAGE_DECODE) {
+    if (io && (io->out.n > 0 || io->val_mask)) {  // pull the cotangent back through inverse_data(...) .* val_mask
+      MGN_CUDA_TRY(prepare_dout(io->out, io->val_mask, dout, N, m->cfg.out_dim, w.dout_f, st));
+      dout = w.dout_f;
+    }
     // Decoder: d_nf = d(out)/d(nf[mps])
     MGN_CUDA_TRY(mlp_backward(m->mlps[di], params, dparams, op1(w.nf[mps], nullptr, D, D), N,
                               w.saved[di], dout, m->cfg.out_dim, nullptr, 0, nullptr, w, w.d_nf, st));
@@ -291,6 +313,7 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
     MGN_CUDA_TRY(mlp_backward(m->mlps[0], params, dparams,
                               op1(nf, nullptr, m->cfg.node_in, m->cfg.node_in), N, w.saved[0], w.d_nf, D,
                               nullptr, 0, nullptr, w, dnf, st));
+    if (io && dnf) MGN_CUDA_TRY(finish_dx(io->node, N, dnf, st));  // transposed normalisers: gradient w.r.t. the raw fields
     MGN_TRY(done(0));
   }
   return MGN_OK;
@@ -298,14 +321,14 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
 
 int32_t forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                 const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
-                cudaStream_t st) {
-  return forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, kStageAll, st);
+                cudaStream_t st, const FusedIo* io) {
+  return forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, kStageAll, st, io);
 }
 
 int32_t backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                  const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                 size_t ws_bytes, cudaStream_t st, GradHook* hook) {
-  return backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st, hook);
+                 size_t ws_bytes, cudaStream_t st, GradHook* hook, const FusedIo* io) {
+  return backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st, hook, io);
 }
 
 // Rows of the node latent / its gradient, for the halo exchange of graph-partitioned meshes.

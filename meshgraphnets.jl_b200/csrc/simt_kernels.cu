@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "features.cuh"
 
 namespace mgn {
 
@@ -588,16 +589,6 @@ norm_finish_kernel(const float* __restrict__ partial, int nblk, int64_t rows, in
     state[2 * F] += (float)rows;
     state[2 * F + 1] += 1.f;
   }
-}
-
-__device__ __forceinline__ void online_mean_std(const float* state, int F, int f, float std_eps,
-                                                float& mean, float& sd) {
-  const float cnt = fmaxf(state[2 * F], 1.f);
-  mean = state[f] / cnt;
-  const float var = state[F + f] / cnt - mean * mean;
-  float s = sqrtf(var);
-  if (!(s == s)) s = std_eps;  // NaN from a slightly negative variance
-  sd = fmaxf(s, std_eps);
 }
 
 __global__ void norm_apply_kernel(const float* __restrict__ x, int64_t rows, int F,

@@ -1,6 +1,7 @@
 // tcgen05 (5th-gen tensor core) path: bf16 operands, fp32 accumulation in TMEM.
 #pragma once
 #include "common.cuh"
+#include "features.cuh"
 
 namespace mgn {
 
@@ -12,17 +13,18 @@ void tc_model_free(mgn_model* m);
 int32_t tc_workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training, size_t* bytes);
 int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                    const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
-                   cudaStream_t st);
+                   cudaStream_t st, const FusedIo* io = nullptr);
 int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                     const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                    size_t ws_bytes, cudaStream_t st, GradHook* hook = nullptr);
+                    size_t ws_bytes, cudaStream_t st, GradHook* hook = nullptr, const FusedIo* io = nullptr);
 int32_t tc_backward_scratch_bytes(const mgn_model* m, const mgn_graph* g, size_t* bytes);
 int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                          const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
-                         cudaStream_t st);
+                         cudaStream_t st, const FusedIo* io = nullptr);
 int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                           const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                          size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook = nullptr);
+                          size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook = nullptr,
+                          const FusedIo* io = nullptr);
 int32_t tc_halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,
                      int step, const int32_t* rows, int64_t n_rows, void* buf, int op, cudaStream_t st);
 
@@ -76,9 +78,9 @@ struct FwdParams {
   const __nv_bfloat16 *x0, *x1, *x2;  // row-major [rows][128] bf16
   const __nv_bfloat16* x2_img;        // IN_GATHER3: the third segment as tile images [tile][2][16 KB] (bulk copies)
   const int32_t *idx0, *idx1;         // IN_GATHER3: rows of x0 for K-blocks {0,1} / {2,3}
-  const float* raw;                   // IN_RAW: fp32 [rows][raw_F]
+  FeatRecipe feat;                    // IN_RAW: the raw fp32 features as a recipe (features.cuh): normalise + concat on the fly
   const int32_t* raw_idx;             // IN_RAW: optional row gather (CSR perm)
-  int raw_F;
+  int raw_F;                          // == feat.F
   // layers
   int n_layers;
   int nkb[kMaxLayers];                // K-blocks (64 wide) of each layer
@@ -97,6 +99,8 @@ struct FwdParams {
   __nv_bfloat16* agg_bf16;            // [nodes][128]
   float* out;                         // FIN_LINEAR: [rows][out_dim]
   int out_dim;
+  FeatRecipe out_feat;                // FIN_LINEAR: inverse_data per output column (n == 0: none) ...
+  const float* val_mask;              // ... and `.* val_mask` [rows][out_dim] (nullable)   <- src/solve.jl:205-218
   // training saves (nullptr when not training)
   __nv_bfloat16* save_h[kMaxLayers - 1];  // image [tile][2 tiles]
   __nv_bfloat16* save_xhat;               // image [tile][2 tiles]
@@ -183,11 +187,14 @@ struct Pieces { Piece p[kMaxPieces]; int n; };
 cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st);
 // Decoder head: dZ_{L-2} = (dout W_{L-1}^T) .* (H_{L-2} > 0) as an image, plus per-tile partials of
 // dW_{L-1} [128][od], db_{L-1} [od] and db_{L-2} [128]  (stride 128*od + od + 128 floats per tile).
+// out_feat / val_mask: the cotangent is first pulled back through `inverse_data(...) .* val_mask` (fused output).
 cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,
-                             int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, cudaStream_t st);
+                             int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, const FeatRecipe& out_feat,
+                             const float* val_mask, cudaStream_t st);
 // Encoder input layer: dW_0 [F][128] per-tile partials from the dZ_0 image and the raw fp32 features;
 // d_raw [rows][F] = dZ_0 W_0^T when requested.
-cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const int32_t* raw_idx, int F,
+// raw features come from a recipe; d_raw is the gradient w.r.t. the recipe's SOURCE columns (transposed normaliser applied).
+cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const FeatRecipe& feat, const int32_t* raw_idx, int F,
                               const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
                               float* partial, float* d_raw, cudaStream_t st);
 // d_nf[v] += recv_sum[v] + sum over CSC row v of dxs[csc_slot[j]]  (adjoints of the receiver and sender gathers;

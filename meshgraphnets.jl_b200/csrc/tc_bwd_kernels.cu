@@ -911,14 +911,26 @@ __global__ void __launch_bounds__(128) decoder_head_kernel(const float* __restri
                                                            const float* __restrict__ w_last,
                                                            const __nv_bfloat16* __restrict__ h_img, int64_t M,
                                                            __nv_bfloat16* __restrict__ z_img,
-                                                           float* __restrict__ partial) {
+                                                           float* __restrict__ partial, const FeatRecipe out_feat,
+                                                           const float* __restrict__ val_mask) {
   __shared__ float dout_s[128 * 16];
+  __shared__ FeatCol otab[16];
   const int tile = blockIdx.x, c = threadIdx.x;
   const int64_t row0 = (int64_t)tile * kTile;
   const int cnt = (int)min((int64_t)kTile, M - row0);
+  const bool fused_out = out_feat.n > 0;
+  if (fused_out) {
+    feat_table(out_feat, otab, c, 128);
+    __syncthreads();
+  }
   for (int i = c; i < 128 * od; i += 128) {
     const int r = i / od;
-    dout_s[i] = r < cnt ? dout[row0 * od + i] : 0.f;
+    float d = r < cnt ? dout[row0 * od + i] : 0.f;
+    if (r < cnt) {  // pullback of `inverse_data(o_norm, out) .* val_mask` (src/solve.jl:205-218)
+      if (val_mask) d = d * val_mask[row0 * od + i];
+      if (fused_out) d = out_vjp(otab[i - r * od], d);
+    }
+    dout_s[i] = d;
   }
   float wc[16], dw[16];
 #pragma unroll
@@ -963,7 +975,7 @@ __global__ void __launch_bounds__(128) decoder_head_kernel(const float* __restri
 // One CTA per tile.  Phase 1 (thread == output column): dW_0[f][c] partials.  Phase 2 (thread == row):
 // d_raw[row][f] = sum_c dZ_0[row][c] W_0[f][c].
 __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16* __restrict__ dz0,
-                                                            const float* __restrict__ raw,
+                                                            const FeatRecipe feat,
                                                             const int32_t* __restrict__ raw_idx, int F,
                                                             const float* __restrict__ w0, int64_t M,
                                                             const int32_t* __restrict__ trs,
@@ -971,10 +983,13 @@ __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16*
   extern __shared__ float es[];
   float* z_s = es;               // [128][129]
   float* x_s = es + 128 * 129;   // [128][F]
+  __shared__ FeatCol ftab[kMaxFeat];
   const int tile = blockIdx.x, t = threadIdx.x;
+  feat_table(feat, ftab, t, 128);
   int64_t row0;
   int cnt;
   tile_rows(trs, M, tile, row0, cnt);
+  __syncthreads();  // ftab complete
   const uint8_t* zb = reinterpret_cast<const uint8_t*>(dz0) + (size_t)tile * kImg;
   for (int i = t; i < 128 * 16; i += 128) {  // 16-byte chunks of the image
     const int r = i >> 4, ch = i & 15;
@@ -991,7 +1006,7 @@ __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16*
     float v = 0.f;
     if (r < cnt) {
       const int64_t src = raw_idx ? (int64_t)raw_idx[row0 + r] : row0 + r;
-      v = raw[src * F + f];
+      v = feat_eval(ftab[f], src);
     }
     x_s[i] = v;
   }
@@ -1013,7 +1028,7 @@ __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16*
     for (int f = 0; f < F; ++f) {
       float s = 0.f;
       for (int c = 0; c < 128; ++c) s = fmaf(z_s[t * 129 + c], w0[f * 128 + c], s);
-      d_raw[(row0 + t) * F + f] = s;
+      d_raw[(row0 + t) * F + f] = feat_vjp(ftab[f], s);   // pullback of the normaliser (identity recipe: s * 1)
     }
   }
 }
@@ -1124,14 +1139,15 @@ cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st) {
 }
 
 cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,
-                             int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, cudaStream_t st) {
+                             int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, const FeatRecipe& out_feat,
+                             const float* val_mask, cudaStream_t st) {
   if (n_tiles == 0) return cudaSuccess;
   ProfScope ps(TAG_TC_MISC, st);
-  decoder_head_kernel<<<n_tiles, 128, 0, st>>>(dout, out_dim, w_last, h_img, M, z_img, partial);
+  decoder_head_kernel<<<n_tiles, 128, 0, st>>>(dout, out_dim, w_last, h_img, M, z_img, partial, out_feat, val_mask);
   return cudaGetLastError();
 }
 
-cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const int32_t* raw_idx, int F,
+cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const FeatRecipe& feat, const int32_t* raw_idx, int F,
                               const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
                               float* partial, float* d_raw, cudaStream_t st) {
   if (n_tiles == 0) return cudaSuccess;
@@ -1143,7 +1159,7 @@ cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const float* raw, const 
   });
   if (ce != cudaSuccess) return ce;
   ProfScope ps(TAG_TC_MISC, st);
-  encoder_input_kernel<<<n_tiles, 128, smem, st>>>(dz0, raw, raw_idx, F, w0, M, tile_row_start, partial, d_raw);
+  encoder_input_kernel<<<n_tiles, 128, smem, st>>>(dz0, feat, raw_idx, F, w0, M, tile_row_start, partial, d_raw);
   return cudaGetLastError();
 }
 

@@ -36,7 +36,9 @@ struct Lay {
   static constexpr uint32_t kLn = kBias + kMaxLayers * 512;    // scale[128], bias[128]
   static constexpr uint32_t kRp = kLn + 1024;                  // tile-local CSR row pointer, 132 ints
   static constexpr uint32_t kStat = kRp + 132 * 4;             // EW = 8: LayerNorm partial sums [2 halves][128 rows] float2
-  static constexpr uint32_t kBar = kStat + 2 * 128 * 8;        // full[RING], empty[RING], acc_full, epi_done
+  static constexpr uint32_t kFeat = kStat + 2 * 128 * 8;       // FeatCol[kMaxFeat]: raw-feature recipe per column (IN_RAW)
+  static constexpr uint32_t kOutF = kFeat + kMaxFeat * 32;     // FeatCol[16]: inverse_data per output column (FIN_LINEAR)
+  static constexpr uint32_t kBar = kOutF + 16 * 32;            // full[RING], empty[RING], acc_full, epi_done
   static constexpr uint32_t kTmem = kBar + (2 * RING + 2) * 8;
   static constexpr uint32_t kTotal = kTmem + 16;
   static constexpr uint32_t kLaunch = kTotal + 1024;           // slack for the 1024 B alignment
@@ -102,6 +104,7 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
   constexpr int kRing = RING;
   constexpr uint32_t kSmemRing = L_::kRing, kSmemH = L_::kH, kSmemBias = L_::kBias, kSmemLn = L_::kLn, kSmemRp = L_::kRp,
                      kSmemStat = L_::kStat, kSmemBar = L_::kBar, kSmemTmem = L_::kTmem;
+  static_assert(sizeof(FeatCol) == 32, "FeatCol is 32 bytes");
   constexpr int kThreads = 32 * (EW + NP + 1);
   constexpr int kEpi = 32 * EW;        // epilogue threads
   constexpr int kHalves = EW / 4;      // threads per tile row
@@ -114,6 +117,8 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
   float* bias_s = reinterpret_cast<float*>(smem + kSmemBias);
   float* ln_s = reinterpret_cast<float*>(smem + kSmemLn);
   int* rp_s = reinterpret_cast<int*>(smem + kSmemRp);
+  FeatCol* ftab = reinterpret_cast<FeatCol*>(smem + L_::kFeat);
+  FeatCol* otab = reinterpret_cast<FeatCol*>(smem + L_::kOutF);
   const uint32_t bar0 = s_base + kSmemBar;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
@@ -122,6 +127,8 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
+  if (p.in_mode == IN_RAW) feat_table(p.feat, ftab, tid, kThreads);
+  if (p.fin_mode == FIN_LINEAR && p.out_feat.n > 0) feat_table(p.out_feat, otab, tid, kThreads);
 
   // ---- one-time setup
   for (int i = tid; i < L * 128; i += kThreads) {
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
 #pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     const int f = kb * 64 + c * 8 + j;
-                    v[j] = (ok && f < p.raw_F) ? p.raw[src_row * p.raw_F + f] : 0.f;
+                    v[j] = (ok && f < p.raw_F) ? feat_eval(ftab[f], src_row) : 0.f;
                   }
                   st_shared_v4(dst + t128_off(r, c), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
@@ -319,8 +326,15 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
           if (half == 0) tmem_ld16(t_lane, v);  // warp-uniform: a warp belongs to one half
           tc_fence_before();
           mbar_arrive(epi_done);
-          if (half == 0 && row < cnt)
-            for (int j = 0; j < p.out_dim; ++j) p.out[(row0 + row) * p.out_dim + j] = v[j] + bias_s[l * 128 + j];
+          if (half == 0 && row < cnt) {
+            const bool fused_out = p.out_feat.n > 0;
+            for (int j = 0; j < p.out_dim; ++j) {
+              float y = v[j] + bias_s[l * 128 + j];
+              if (fused_out) y = out_eval(otab[j], y);                                   // inverse_data (src/solve.jl:205-210)
+              if (p.val_mask) y = y * p.val_mask[(row0 + row) * p.out_dim + j];          // .* val_mask (src/solve.jl:218)
+              p.out[(row0 + row) * p.out_dim + j] = y;
+            }
+          }
           continue;
         }
         // the shared activation tile is about to be overwritten: every thread must be done reading the

@@ -199,7 +199,7 @@ constexpr int kStageAll = -3;
 
 int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                          const float* ef, float* out, void* ws, size_t ws_bytes, bool training, int stage,
-                         cudaStream_t st) {
+                         cudaStream_t st, const FusedIo* io) {
   if (!g->tiles_ok)
     return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
   TcWorkspace w;
@@ -219,7 +219,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.n_tiles = node_tiles;
       p.M = N;
       p.in_mode = IN_RAW;
-      p.raw = nf;
+      p.feat = io ? io->node : identity_recipe(nf, m->cfg.node_in);
       p.raw_F = m->cfg.node_in;
       p.ksteps0 = (m->cfg.node_in + 15) / 16;
       p.fin_mode = FIN_LN;
@@ -234,7 +234,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.M = E;
       p.tile_row_start = g->tile_row_start;
       p.in_mode = IN_RAW;
-      p.raw = ef;
+      p.feat = io ? io->edge : identity_recipe(ef, m->cfg.edge_in);
       p.raw_idx = g->perm;
       p.raw_F = m->cfg.edge_in;
       p.ksteps0 = (m->cfg.edge_in + 15) / 16;
@@ -298,6 +298,10 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
     p.fin_mode = FIN_LINEAR;
     p.out = out;
     p.out_dim = m->cfg.out_dim;
+    if (io) {
+      p.out_feat = io->out;
+      p.val_mask = io->val_mask;
+    }
     MGN_CUDA_TRY(mlp_forward_tc(p, st));
   }
   return MGN_OK;
@@ -305,8 +309,8 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
 
 int32_t tc_forward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                    const float* ef, float* out, void* ws, size_t ws_bytes, bool training,
-                   cudaStream_t st) {
-  return tc_forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, kStageAll, st);
+                   cudaStream_t st, const FusedIo* io) {
+  return tc_forward_stage(m, g, params, nf, ef, out, ws, ws_bytes, training, kStageAll, st, io);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -391,7 +395,7 @@ int32_t run_input(const BwdCtx& c, size_t mi, InputParams& p, Pieces& pc) {
   return MGN_OK;
 }
 
-int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const float* raw, const int32_t* raw_idx,
+int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const FeatRecipe& raw, const int32_t* raw_idx,
                           float* d_raw, Pieces& pc) {
   const MlpLayout& L = c.m->mlps[mi];
   const int n_tiles = edge_rows ? c.g->n_edge_tiles : (int)((c.g->N + kTile - 1) / kTile);
@@ -408,7 +412,7 @@ int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const floa
 
 int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                           const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                          size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook) {
+                          size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook, const FusedIo* io) {
   auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi) : MGN_OK; };
   if (!g->tiles_ok)
     return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
@@ -427,8 +431,9 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     // ---- Decoder (no LayerNorm): last Dense on CUDA cores, the rest on the tensor cores
     const size_t di = m->mlps.size() - 1;
     const MlpLayout& L = m->mlps[di];
+    FeatRecipe no_out{};
     MGN_CUDA_TRY(decoder_head_bwd(dout, od, params + L.w_off[nd - 1], w.saves[di].h[nd - 2], node_tiles, N, b.ztop,
-                                  b.partial_misc, st));
+                                  b.partial_misc, io ? io->out : no_out, io ? io->val_mask : nullptr, st));
     Pieces pc{};
     const int64_t hs = (int64_t)128 * od + od + 128;
     pc.p[pc.n++] = {b.partial_misc, hs, node_tiles, dparams + L.w_off[nd - 1], (int64_t)128 * od};
@@ -503,7 +508,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     if (mps > 0 && E > 0) {
       Pieces pc{};
       MGN_TRY(run_chain(c, 1, true, b.d_ef, nullptr, nullptr, pc));
-      MGN_TRY(run_encoder_input(c, 1, true, ef, g->perm, nullptr, pc));
+      MGN_TRY(run_encoder_input(c, 1, true, io ? io->edge : identity_recipe(ef, m->cfg.edge_in), g->perm, nullptr, pc));
     } else {
       const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
@@ -511,7 +516,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     MGN_TRY(done(1));
     Pieces pc{};
     MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr, pc));
-    MGN_TRY(run_encoder_input(c, 0, false, nf, nullptr, dnf, pc));
+    MGN_TRY(run_encoder_input(c, 0, false, io ? io->node : identity_recipe(nf, m->cfg.node_in), nullptr, dnf, pc));
     MGN_TRY(done(0));
   }
   return MGN_OK;
@@ -519,8 +524,8 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
 
 int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                     const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
-                    size_t ws_bytes, cudaStream_t st, GradHook* hook) {
-  return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st, hook);
+                    size_t ws_bytes, cudaStream_t st, GradHook* hook, const FusedIo* io) {
+  return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, kStageAll, st, hook, io);
 }
 
 int32_t tc_halo_rows(const mgn_model* m, const mgn_graph* g, void* ws, size_t ws_bytes, bool training, int what,

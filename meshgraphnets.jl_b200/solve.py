@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from ._lib import MgnError
+from .fused import FusedGraph, forward_fused
 from .graph import build_graph
 from .shooting import RK_TABLEAUS, DeviceAlgebra
 
@@ -20,7 +21,37 @@ _alg = DeviceAlgebra()
 
 def ode_step(x, p, t):
     """src/solve.jl:188-219.  x is [N, sum(target dims)]; p = (mgn, ps, inputs, fields, meta,
-    target_fields, target_dict, node_type, edge_features, senders, receivers, val_mask)."""
+    target_fields, target_dict, node_type, edge_features, senders, receivers, val_mask).
+    ONE fused model call (mgn_forward_fused): the state columns, the other input fields and the one-hot node types are
+    normalised and concatenated while the encoder stages its operand, `inverse_data(o_norm, out) .* val_mask` runs in
+    the decoder's epilogue; the normalisers' accumulate branch (they still fire in the reference's rollout) is two
+    launches for all of them.  ode_step_unfused is the operation-by-operation form (same values)."""
+    mgn, ps, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats, senders, receivers, val_mask = p
+    x = x.contiguous()
+    offs, off = {}, 0
+    for k in target_fields:
+        offs[k] = off
+        off += target_dict[k]
+    blocks = []
+    for f in fields:
+        if f in offs:
+            blocks.append((mgn.n_norm[f], x, offs[f], target_dict[f]))
+        else:
+            v = inputs[f]
+            v = (v[0] if v.dim() == 3 else v).contiguous()
+            blocks.append((mgn.n_norm[f], v, 0, v.shape[1]))
+    # the reference evaluates the node_type normaliser first (graph.jl:80); it lands last (graph.jl:86)
+    blocks.append((mgn.n_norm["node_type"], node_type, 0, node_type.shape[1]))
+    out_blocks = [(mgn.o_norm[tf], int(meta["features"][tf]["dim"])) for tf in target_fields]
+    fg = FusedGraph(blocks, (mgn.e_norm, edge_feats, 0, edge_feats.shape[1]), senders, receivers, node_type.shape[0],
+                    out_blocks, val_mask)
+    fg.accumulate()
+    return forward_fused(mgn.model, fg, ps)
+
+
+def ode_step_unfused(x, p, t):
+    """ode_step as the sequence of separate operations of src/solve.jl:188-219 (build_graph, model, inverse_data per
+    target field, val_mask product)."""
     mgn, ps, inputs, fields, meta, target_fields, target_dict, node_type, edge_feats, senders, receivers, val_mask = p
     offset = 0
     for k in target_fields:
