@@ -60,6 +60,15 @@ typedef struct mgn_model_config {
   int32_t hidden_layers; /* Dense layers per MLP = hidden_layers + 2 (Args :38)         */
   float ln_eps;          /* Lux.LayerNorm epsilon, 1e-5                                 */
   int32_t compute_mode;  /* MGN_COMPUTE_*                                               */
+  /* GraphNetCore.jl is not vendored in the reference tree, so three of its internals are recalled, not read
+   * (SURVEY.md section 9).  Each is a field here: if oracle/julia/dump_reference.jl disagrees, flip the field - no
+   * kernel changes.  All-zero = the recalled defaults. */
+  int32_t dense_layers;  /* Dense layers per MLP; 0 = hidden_layers + 2 (recalled build_mlp), else explicit
+                          * (hidden_layers + 1 would be DeepMind's _make_mlp).  2..4 in MGN_COMPUTE_BF16.          */
+  int32_t ln_scale_first; /* LayerNorm parameter order in the flat vector: 0 = (bias, scale) (recalled Lux 0.5
+                          * ComponentArray order), 1 = (scale, bias)                                              */
+  int32_t aggregate_post_residual; /* 0 = scatter-sum the NEW messages m (DeepMind / recalled GraphNetCore order);
+                          * 1 = scatter-sum ef + m: not built - MGN_ERR_UNSUPPORTED names the kernels to change    */
 } mgn_model_config;
 
 /* One tensor of the flat Float32 parameter vector (mirrors the ComponentArray `mgn.ps` that

@@ -32,6 +32,7 @@ class ModelConfig(C.Structure):
         ("node_in", C.c_int32), ("edge_in", C.c_int32), ("out_dim", C.c_int32),
         ("latent", C.c_int32), ("mps", C.c_int32), ("hidden_layers", C.c_int32),
         ("ln_eps", C.c_float), ("compute_mode", C.c_int32),
+        ("dense_layers", C.c_int32), ("ln_scale_first", C.c_int32), ("aggregate_post_residual", C.c_int32),
     ]
 
 

@@ -311,9 +311,12 @@ class Model:
     (src/solve.jl:200).  Holds the mgn_model handle and a per-graph workspace."""
 
     def __init__(self, node_in, edge_in, out_dim, mps, layer_size, hidden_layers, ln_eps=1e-5,
-                 compute_mode=COMPUTE_FP32):
+                 compute_mode=COMPUTE_FP32, dense_layers=0, ln_scale_first=False, aggregate_post_residual=False):
+        """The last three arguments are the recalled GraphNetCore internals exposed as switches (SURVEY.md section 9,
+        mgn_model_config): Dense layers per MLP (0 = hidden_layers + 2), LayerNorm parameter order, aggregation order."""
         self.cfg = ModelConfig(int(node_in), int(edge_in), int(out_dim), int(layer_size), int(mps),
-                               int(hidden_layers), float(ln_eps), int(compute_mode))
+                               int(hidden_layers), float(ln_eps), int(compute_mode), int(dense_layers),
+                               int(bool(ln_scale_first)), int(bool(aggregate_post_residual)))
         h = C.c_void_p()
         call("mgn_model_create", C.byref(self.cfg), C.byref(h))
         self._h = h

@@ -83,11 +83,15 @@ static void add_mlp(mgn_model* m, const std::string& name, int in_dim, int out_d
     off += L.out[l];
   }
   if (ln) {
-    // Lux 0.5 LayerNorm parameters are (bias, scale) in that order (recalled)
-    L.ln_bias_off = off;
-    off += out_dim;
-    L.ln_scale_off = off;
-    off += out_dim;
+    // Lux 0.5 LayerNorm parameters are (bias, scale) in that order (recalled); cfg.ln_scale_first flips it
+    if (m->cfg.ln_scale_first) {
+      L.ln_scale_off = off;
+      L.ln_bias_off = off + out_dim;
+    } else {
+      L.ln_bias_off = off;
+      L.ln_scale_off = off + out_dim;
+    }
+    off += 2 * out_dim;
   }
   m->mlps.push_back(L);
 }
@@ -287,6 +291,14 @@ int32_t mgn_model_create(const mgn_model_config* cfg, mgn_model** out) {
   MGN_REQUIRE(cfg->out_dim <= 128, "model_create: out_dim must be <= 128");
   MGN_REQUIRE(cfg->mps >= 0 && cfg->hidden_layers >= 0 && cfg->hidden_layers + 2 <= kMaxDense,
               "model_create: bad mps / hidden_layers");
+  MGN_REQUIRE(cfg->dense_layers == 0 || (cfg->dense_layers >= 2 && cfg->dense_layers <= kMaxDense),
+              "model_create: dense_layers must be 0 (= hidden_layers + 2) or in [2, 8]");
+  MGN_REQUIRE(cfg->ln_scale_first == 0 || cfg->ln_scale_first == 1, "model_create: ln_scale_first must be 0 or 1");
+  if (cfg->aggregate_post_residual != 0)
+    return fail(MGN_ERR_UNSUPPORTED,
+                "model_create: aggregate_post_residual = 1 is not built: the aggregation would have to run after the "
+                "residual add (segsum_tile call in mlp_fwd_kernel / segment_sum in pipeline.cu) and the edge MLP's "
+                "backward head would have to route d_agg[recv] into the residual path as well (run_chain dy_b)");
   MGN_REQUIRE(cfg->compute_mode == MGN_COMPUTE_FP32 || cfg->compute_mode == MGN_COMPUTE_BF16,
               "model_create: unknown compute_mode");
   if (cfg->compute_mode == MGN_COMPUTE_BF16)
@@ -347,8 +359,13 @@ int32_t mgn_model_param_layout(const mgn_model* m, mgn_param_entry* entries, int
       put(L.name + ".dense" + std::to_string(l + 1) + ".bias", L.b_off[l], L.out[l], 1);
     }
     if (L.layer_norm) {
-      put(L.name + ".layernorm.bias", L.ln_bias_off, L.out_dim, 1);
-      put(L.name + ".layernorm.scale", L.ln_scale_off, L.out_dim, 1);
+      if (m->cfg.ln_scale_first) {
+        put(L.name + ".layernorm.scale", L.ln_scale_off, L.out_dim, 1);
+        put(L.name + ".layernorm.bias", L.ln_bias_off, L.out_dim, 1);
+      } else {
+        put(L.name + ".layernorm.bias", L.ln_bias_off, L.out_dim, 1);
+        put(L.name + ".layernorm.scale", L.ln_scale_off, L.out_dim, 1);
+      }
     }
   }
   *n = k;

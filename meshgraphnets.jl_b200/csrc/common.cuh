@@ -110,7 +110,7 @@ struct mgn_model {
   mgn::TuneKnobs knobs;                    // environment knobs, frozen at creation
   std::vector<mgn::MlpLayout> mlps;  // encoder.node, encoder.edge, (edge, node) x mps, decoder
   int64_t n_params = 0;
-  int n_dense() const { return cfg.hidden_layers + 2; }
+  int n_dense() const { return cfg.dense_layers > 0 ? cfg.dense_layers : cfg.hidden_layers + 2; }
 };
 
 struct mgn_graph {

@@ -240,12 +240,15 @@ class ModelConfig:
     mps: int = 15           # src/MeshGraphNets.jl:36
     hidden_layers: int = 2  # src/MeshGraphNets.jl:38
     ln_eps: float = 1e-5    # Lux 0.5 LayerNorm default epsilon (recalled)
+    # the recalled internals as switches (mgn_model_config of include/mgn_b200.h)
+    dense_layers: int = 0          # 0 = hidden_layers + 2
+    ln_scale_first: bool = False   # flat order of the LayerNorm parameters: (bias, scale) recalled
 
     @property
     def n_dense(self):
         # recalled build_mlp: Dense(in,latent,relu), hidden_layers x Dense(latent,latent,relu),
         # Dense(latent,out)
-        return self.hidden_layers + 2
+        return self.dense_layers if self.dense_layers > 0 else self.hidden_layers + 2
 
 
 @dataclass
@@ -280,8 +283,8 @@ def mlp_specs(cfg: ModelConfig):
             i, o = dims[l], dims[l + 1]
             s.dense.append((off, off + i * o, i, o))
             off += i * o + o
-        if s.layer_norm:
-            s.ln = (off, off + s.out_dim)
+        if s.layer_norm:   # s.ln = (bias offset, scale offset)
+            s.ln = (off + s.out_dim, off) if cfg.ln_scale_first else (off, off + s.out_dim)
             off += 2 * s.out_dim
         s.size = off - s.offset
     return specs, off

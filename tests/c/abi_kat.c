@@ -69,14 +69,14 @@ int main(void) {
   CHECK(mgn_one_hot(NULL, 3, 7, 1, NULL) == MGN_ERR_INVALID);
   CHECK(mgn_model_create(NULL, NULL) == MGN_ERR_INVALID);
   {
-    mgn_model_config cfg = {9, 3, 2, 64, 15, 2, 1e-5f, MGN_COMPUTE_BF16};   /* bf16 mode needs latent 128 */
+    mgn_model_config cfg = {9, 3, 2, 64, 15, 2, 1e-5f, MGN_COMPUTE_BF16, 0, 0, 0};   /* bf16 mode needs latent 128 */
     mgn_model* m = NULL;
     CHECK(mgn_model_create(&cfg, &m) == MGN_ERR_INVALID && m == NULL);
     CHECK(mgn_last_error(msg, sizeof msg) == MGN_OK && strstr(msg, "128") != NULL);
   }
   /* the parameter table of the reference configuration (fp32 mode needs no device to be built) */
   {
-    mgn_model_config cfg = {9, 3, 2, 128, 15, 2, 1e-5f, MGN_COMPUTE_FP32};
+    mgn_model_config cfg = {9, 3, 2, 128, 15, 2, 1e-5f, MGN_COMPUTE_FP32, 0, 0, 0};
     mgn_model* m = NULL;
     int64_t count = 0;
     int32_t n = 0;
