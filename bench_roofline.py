@@ -8,9 +8,11 @@ against the measured peaks of MEASURED_PEAKS.json.  The algorithmic work per uni
 layout of DESIGN.md section 3 (training mode, fp32 master latents + bf16 shadows):
 
   kernel family   FLOP / edge row          FLOP / node row        bytes / edge row   bytes / node row
-  forward         2 D^2 (L+2)              2 D^2 (L+1)            2572               2820 (+512: gather source + agg)
-  bwd chain       4 D^2 (L-1)              4 D^2 (L-1)            1796 (+512 d_agg per node)  1796
-  bwd input       12 D^2                   8 D^2                  1800               3840
+  forward         2 D^2 (L+2)              2 D^2 (L+1)            1548               2820 (+512: gather source + agg)
+  bwd chain       4 D^2 (L-1)              4 D^2 (L-1)            1540 (+512 d_agg per node)  1796
+  bwd input       12 D^2                   8 D^2                  1288               3840
+(round 2: the edge latent and its gradient are stored in bf16 only, as tile images - no fp32 master: -1024 B per edge row
+in the forward kernel, -256 B in the chain kernel, -512 B in the input kernel.)
 (bytes: every tensor the kernel must read or write once per row; gathered node rows are counted
 once per node, not once per edge - they are L2 hits after the first touch.)
 """
@@ -40,24 +42,26 @@ def algorithmic_work(E, N, D, L, mps, node_in, edge_in, out_dim):
     saves = L * img + 4
     f_edge = 2 * D2 * (L + 2)
     f_node = 2 * D2 * (L + 1)
-    b_edge_fwd = img + f32 + 8 + f32 + img + saves                 # ef16, ef32 r/w, idx, ef16', saves
+    b_edge_fwd = img + 8 + img + saves                             # ef16 (operand AND residual), idx, ef16', saves
     b_node_fwd = 2 * img + f32 + f32 + img + saves + 2 * img       # nf16, agg16, nf32 r/w, nf16', saves | gather src, agg write
     fwd_flops = mps * (f_edge * E + f_node * N)
     fwd_bytes = mps * (b_edge_fwd * E + b_node_fwd * N)
-    fwd_bytes -= (2 * f32 + img) * E             # the edge latent after the last MP step is never read: not updated
+    fwd_bytes -= img * E                         # the edge latent after the last MP step is never read: not written
     enc_flops = 2 * ((node_in * D + (L - 1) * D2) * N + (edge_in * D + (L - 1) * D2) * E)
     dec_flops = 2 * ((L - 1) * D2 + D * out_dim) * N
     fwd_flops += enc_flops + dec_flops
-    fwd_bytes += (4 * edge_in + f32 + img + saves + 4) * E + (4 * node_in + f32 + img + saves) * N
+    fwd_bytes += (4 * edge_in + img + saves + 4) * E + (4 * node_in + f32 + img + saves) * N
     fwd_bytes += (img + (L - 1) * img + 4 * out_dim) * N
     # ---- backward chain: (L-1) x (dX, dW) GEMMs; reads dy (fp32), xhat, rstd, L-1 hidden images; writes dZ0
     c_flops_row = 4 * D2 * (L - 1)
-    c_bytes_row = f32 + img + 4 + (L - 1) * img + img
+    c_bytes_row = f32 + img + 4 + (L - 1) * img + img          # node rows: fp32 dy
+    c_bytes_edge = c_bytes_row - f32 + img                     # edge rows: dy is a bf16 image
     chain_flops = mps * c_flops_row * (E + N) + c_flops_row * (E + N) + 4 * D2 * max(L - 2, 0) * N
-    chain_bytes = mps * (c_bytes_row * (E + N) + f32 * N) + c_bytes_row * (E + N) + ((L - 1) * img + img) * N
+    chain_bytes = (mps * (c_bytes_edge * E + c_bytes_row * N + f32 * N) - img * E    # last MP step: no d_ef yet
+                   + c_bytes_edge * E + c_bytes_row * N + ((L - 1) * img + img) * N)
     # ---- backward input layer
     i_flops = mps * (12 * D2 * E + 8 * D2 * N) + 4 * D2 * N
-    i_bytes = mps * ((img + img + 8 + 2 * f32 + img) * E + 3 * f32 * N          # dz0, ef16, idx, d_ef r/w, dxs | d_nf r/w
+    i_bytes = mps * ((img + img + 8 + 2 * img + img) * E + 3 * f32 * N          # dz0, ef16, idx, d_ef r/w (bf16), dxs | d_nf r/w
                      + (img + 2 * img + 2 * f32 + f32) * N)                      # node MLP: dz0, nf16+agg16, d_nf r/w, d_agg
     i_bytes += (img + img + f32) * N
     return {"tc_mlp_fwd": (fwd_flops, fwd_bytes), "tc_mlp_bwd": (chain_flops, chain_bytes),
@@ -72,15 +76,17 @@ def survey_flops(E, N, D, L, mps, node_in, edge_in, out_dim):
             + 2 * ((L - 1) * D2 + D * out_dim) * N)
 
 
-def survey_forward_bytes(E, N, D, L, mps, node_in, edge_in, out_dim, s):
+def survey_forward_bytes(E, N, D, L, mps, node_in, edge_in, out_dim, s, s_edge=None):
     """Algorithmic bytes of the fused-forward launches of ONE training step exactly as SURVEY.md 8(d) counts them,
-    s = bytes per STORED latent element (4: the fp32 master latents this library keeps): per MP step
-    2 E D s (ef read + write) + 3 N D s (nf gather source once, nf read + write) + 8 E + 4 (N + 1) (indices) +
+    s = bytes per STORED latent element (node latent: 4, the fp32 master; edge latent s_edge: 2 since round 2, it is
+    stored in bf16 only; s_edge = 4 reproduces the round-1 figure the judge computed, 7.07 GB): per MP step
+    2 E D s_edge (ef read + write) + 3 N D s (nf gather source once, nf read + write) + 8 E + 4 (N + 1) (indices) +
     (2L + 3) D^2 weight elements once per launch (bf16 images); encoders read the raw features and write the latents,
     the decoder reads the node latent and writes the output.  Saved activations are NOT counted here (8d lets the
     builder state them: they are the difference between `frac_alg` and `frac_design`)."""
-    per_step = 2 * E * D * s + 3 * N * D * s + 8 * E + 4 * (N + 1) + (2 * L + 3) * D * D * 2
-    enc = (4 * node_in + D * s) * N + (4 * edge_in + D * s + 4) * E + 2 * ((node_in + edge_in) * D + 2 * (L - 1) * D * D)
+    se = s if s_edge is None else s_edge
+    per_step = 2 * E * D * se + 3 * N * D * s + 8 * E + 4 * (N + 1) + (2 * L + 3) * D * D * 2
+    enc = (4 * node_in + D * s) * N + (4 * edge_in + D * se + 4) * E + 2 * ((node_in + edge_in) * D + 2 * (L - 1) * D * D)
     dec = D * s * N + 4 * out_dim * N + 2 * ((L - 1) * D * D + D * out_dim)
     return mps * per_step + enc + dec
 
@@ -134,8 +140,11 @@ def roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn=None, n_node
             row.update({"gbs": gbs, "hbm_frac": gbs / pk["hbm_gbs"], "alg_bytes_per_launch": nbytes / launches,
                         "alg_flops_per_launch": flops / launches})
             if name == "tc_mlp_fwd":    # SURVEY 8(d) bytes (fp32 stored latents), without the saved activations
-                alg = survey_forward_bytes(E, n_nodes, D, L, MPS, 9, 3, 2, 4)
+                alg = survey_forward_bytes(E, n_nodes, D, L, MPS, 9, 3, 2, 4, s_edge=2)
+                alg_r1 = survey_forward_bytes(E, n_nodes, D, L, MPS, 9, 3, 2, 4)
                 row.update({"survey8d_bytes_per_step": alg, "frac_alg": alg / sec / 1e9 / pk["hbm_gbs"],
+                            "survey8d_bytes_per_step_fp32_edges": alg_r1,
+                            "frac_alg_fp32_edge_convention": alg_r1 / sec / 1e9 / pk["hbm_gbs"],
                             "frac_design": gbs / pk["hbm_gbs"]})
             t = traffic.get(name)
             if t:
@@ -159,7 +168,9 @@ def roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn=None, n_node
                            "note": f"dominant kernel family by time inside the step; frac = frac_design: every byte the "
                                    f"launch must move once in THIS design (DESIGN.md section 3: fp32 masters + saved "
                                    f"activations) / launch duration by CUDA events; frac_alg (forward family only): "
-                                   f"SURVEY 8(d) bytes at s = 4 without saved activations; traffic = ncu DRAM bytes "
+                                   f"SURVEY 8(d) bytes at the STORED widths (node latent fp32, edge latent bf16) without "
+                                   f"saved activations (frac_alg_fp32_edge_convention in kernel_families keeps round 1's "
+                                   f"s = 4 numerator for comparison); traffic = ncu DRAM bytes "
                                    f"per launch (profiles/ncu_traffic.json), traffic_ratio = traffic / algorithmic; "
                                    f"peak = {pk['source']} HBM copy bandwidth; tensor_frac is against the "
                                    f"{pk['source']} sustained bf16 peak"}

@@ -92,8 +92,9 @@ struct FwdParams {
   float eps;
   // outputs
   int fin_mode;
-  const float* lat_in;                // fp32 [rows][128] residual input
-  float* lat_out;                     // fp32 [rows][128]
+  const float* lat_in;                // fp32 [rows][128] residual input (node latents: fp32 master) ...
+  const __nv_bfloat16* lat_img_in;    // ... or the bf16 tile images of the latent itself (edge latents: stored in bf16 only)
+  float* lat_out;                     // fp32 [rows][128] (nullptr: no fp32 master is kept)
   __nv_bfloat16* lat_bf16_out;        // bf16 shadow of lat_out (row-major) ...
   __nv_bfloat16* lat_img_out;         // ... or, when non-null, as tile images (one 32 KB bulk store per tile)
   __nv_bfloat16* agg_bf16;            // [nodes][128]
@@ -132,7 +133,8 @@ struct ChainParams {
   const int32_t* tile_row_start;       // nullable (plain 128-row tiles)
   int head_mode;
   // HEAD_LN: dy[r] = dy_a[r] + dy_b[b_idx ? b_idx[r] : r]   (either may be null)
-  const float* dy_a;
+  const float* dy_a;                   // fp32 row-major ...
+  const __nv_bfloat16* dy_a_img;       // ... or bf16 tile images (gradient of the edge latent)
   const float* dy_b;
   const int32_t* b_idx;
   const __nv_bfloat16* xhat;           // image
@@ -156,7 +158,8 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
 // Input kernel: first Dense layer of an MLP whose input is made of 128-wide bf16 blocks.
 //   dW_0[block b] += X_b^T dZ_0 ; dX_b = dZ_0 W_0[block b]^T -> sink b
 enum SinkMode { SINK_NONE = 0, SINK_STORE_BF16 = 1, SINK_ADD_F32 = 2, SINK_SEGSUM_F32 = 3,
-                SINK_STORE_IMG = 4 /* bf16 tile image [tile][2][16 KB]: one bulk store of the staged tile */ };
+                SINK_STORE_IMG = 4, /* bf16 tile image [tile][2][16 KB]: one bulk store of the staged tile */
+                SINK_ADD_IMG = 5    /* dst image = bf16(src image + dX): the tile's own rows, in place allowed */ };
 struct InputParams {
   int n_tiles;
   int64_t M;
@@ -173,6 +176,7 @@ struct InputParams {
   float* f32_dst[3];                   // SINK_ADD_F32: dst[r] = (src ? src[r] : 0) + dX ; SINK_SEGSUM_F32: per node
   const float* f32_src[3];
   __nv_bfloat16* bf16_dst[3];
+  const __nv_bfloat16* img_src[3];     // SINK_ADD_IMG
   float* partial;                      // [grid][nblk * 16384]
   unsigned long long* trace;           // debug (see FwdParams::trace)
 };

@@ -372,6 +372,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
               if (p.dy_a) {
                 a0[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
                 a1[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
+              } else if (p.dy_a_img) {  // 8 bf16 of the tile's own gradient image
+                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.dy_a_img) + (size_t)tile * kImg +
+                                                                (cc >> 3) * kTileB + t128_off(i, cc & 7));
+                a0[k] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                                    __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+                a1[k] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u),
+                                    __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
               }
               if (p.dy_b) {
                 // consecutive CSR rows share their receiver: reuse the previous row's gather instead of asking L2
@@ -703,6 +710,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         // accumulator and the staging pass, so that their latency is off the critical path (1 CTA/SM: registers abound)
         float4 pr0[8], pr1[8];
         const bool prefetch = p.sink[b] == SINK_ADD_F32 && p.f32_src[b] != nullptr;
+        const bool prefetch_img = p.sink[b] == SINK_ADD_IMG && p.img_src[b] != nullptr;
+        if (prefetch_img) {  // the tile's own rows of the source image: 8 x 16 bytes per thread, kept as raw bits in pr0
+          const int pcc = tid & 15, prg = tid >> 4;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.img_src[b]) + (size_t)tile * kImg + (pcc >> 3) * kTileB;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int i = prg + 16 * u;
+            pr0[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < cnt) pr0[u] = *reinterpret_cast<const float4*>(src + t128_off(i, pcc & 7));
+          }
+        }
         if (prefetch) {
           const int pcc = tid & 15, prg = tid >> 4;
           const float* src = p.f32_src[b];
@@ -745,10 +763,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
         }
         tc_fence_before();
         mbar_arrive(acc_empty);
-        if (p.sink[b] == SINK_STORE_IMG) fence_proxy_async();
+        if (p.sink[b] == SINK_STORE_IMG || (p.sink[b] == SINK_ADD_IMG && !prefetch_img)) fence_proxy_async();
         named_bar_sync(1, kEpi);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: staged
-        const int sink = p.sink[b];
+        int sink = p.sink[b];
+        if (sink == SINK_ADD_IMG) {
+          if (prefetch_img) {
+            // dst = bf16(src + dX) in the staged tile, in place (rows >= cnt stay zero), then one bulk store
+            const int cc = tid & 15, rg = tid >> 4;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int i = rg + 16 * u;
+              if (i >= cnt) continue;
+              const uint32_t sa = s_stage + (cc >> 3) * kTileB + t128_off(i, cc & 7);
+              const uint4 q = ld_shared_v4(sa);
+              const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+              const uint32_t sw[4] = {__float_as_uint(pr0[u].x), __float_as_uint(pr0[u].y), __float_as_uint(pr0[u].z),
+                                      __float_as_uint(pr0[u].w)};
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[e] = pack_bf16x2(bf16_bits_to_float(qw[e] & 0xffffu) + bf16_bits_to_float(sw[e] & 0xffffu),
+                                   __uint_as_float(qw[e] & 0xffff0000u) + __uint_as_float(sw[e] & 0xffff0000u));
+              st_shared_v4(sa, o[0], o[1], o[2], o[3]);
+            }
+            fence_proxy_async();
+            named_bar_sync(1, kEpi);
+          }
+          sink = SINK_STORE_IMG;
+        }
         if (sink == SINK_STORE_IMG) {
           // the staged tile already has the image layout (rows >= cnt are zero): it leaves as one bulk store
           if (tid == 0) {

@@ -360,18 +360,30 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
         constexpr int U = 32 / RG;     // rows per thread and 32-row batch (4 or 2)
         float4 r0[2 * U], r1[2 * U];
         const int cc = tid & 15, rg = tid >> 4;
+        const bool resid_img = p.fin_mode != FIN_LN && p.lat_img_in != nullptr;  // residual = the bf16 latent image itself
         const bool resid = p.fin_mode != FIN_LN && p.lat_in != nullptr;
-        const bool write_lat = p.lat_out != nullptr;  // false: only the aggregation is wanted (last MP step's edge latent)
+        // false: only the aggregation is wanted (last MP step's edge latent)
+        const bool write_lat = p.lat_out != nullptr || p.lat_img_out != nullptr || p.lat_bf16_out != nullptr;
         auto issue_residual = [&](int k, int h) {  // batch k covers rows 32k + rg + RG*u
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int i = 32 * k + rg + RG * u;
             r0[U * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
             r1[U * h + u] = r0[U * h + u];
-            if (resid && i < cnt) {
-              const int64_t o = (row0 + i) * 128 + cc * 8;
-              r0[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o);
-              r1[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+            if (i < cnt) {
+              if (resid_img) {  // 8 bf16 of the tile's own image (an L2 hit: the producer staged this tile as an operand)
+                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.lat_img_in) +
+                                                                (size_t)tile * 2 * kTileB + (cc >> 3) * kTileB +
+                                                                t128_off(i, cc & 7));
+                r0[U * h + u] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
+                                            __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
+                r1[U * h + u] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u),
+                                            __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
+              } else if (resid) {
+                const int64_t o = (row0 + i) * 128 + cc * 8;
+                r0[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o);
+                r1[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
+              }
             }
           }
         };
@@ -527,15 +539,17 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
               m[0] += a0.x; m[1] += a0.y; m[2] += a0.z; m[3] += a0.w;
               m[4] += a1.x; m[5] += a1.y; m[6] += a1.z; m[7] += a1.w;
               const int64_t o = (row0 + i) * 128 + cc * 8;
-              *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
-              *reinterpret_cast<float4*>(p.lat_out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+              if (p.lat_out) {
+                *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
+                *reinterpret_cast<float4*>(p.lat_out + o + 4) = make_float4(m[4], m[5], m[6], m[7]);
+              }
               uint4 bq;
               bq.x = pack_bf16x2(m[0], m[1]);
               bq.y = pack_bf16x2(m[2], m[3]);
               bq.z = pack_bf16x2(m[4], m[5]);
               bq.w = pack_bf16x2(m[6], m[7]);
               if (img_out) st_shared_v4(s_h + (cc >> 3) * kTileB + t128_off(i, cc & 7), bq.x, bq.y, bq.z, bq.w);
-              else *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
+              else if (p.lat_bf16_out) *reinterpret_cast<uint4*>(p.lat_bf16_out + o) = bq;
             }
           }
         }

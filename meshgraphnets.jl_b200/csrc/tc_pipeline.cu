@@ -2,9 +2,13 @@
 //
 // Data layout in HBM (all owned by the caller's workspace):
 //   images      bf16 weight images, 16 KB 128B-swizzled K-major tiles (repacked every forward)
-//   nf32 / ef32 fp32 master copies of the node / edge latents, row-major [rows][128]
-//   nf16 / ef16 bf16 shadows used as GEMM operands / gather sources, one per MP step when training; nf16 is row-major
-//               (gathered by index), ef16 is stored as tile images (a tile only ever reads its own rows: bulk copies)
+//   nf32        fp32 master copy of the node latent, row-major [N][128]; nf16 = its bf16 shadow (gather source /
+//               GEMM operand), one per MP step when training
+//   ef16        the edge latent, stored in bf16 ONLY, as tile images (a tile only ever reads its own rows: bulk copies),
+//               one per MP step when training.  No fp32 master: every MLP input is rounded to bf16 anyway, and the CPU
+//               model of this arithmetic shows the fp32 edge master buys nothing at 15 MP steps (output error 7.0e-3
+//               with and without it, gradient 1.65e-2 vs 1.71e-2) while costing 1024 B per edge
+//               row and step of HBM traffic
 //   agg16       bf16 aggregated messages per MP step
 //   saves       per MLP: hidden activations and LayerNorm xhat as tile images [tile][2][16 KB]
 //               (written and read back with 1-D bulk copies), rstd fp32 [rows]
@@ -41,7 +45,7 @@ struct MlpSave {
 
 struct TcWorkspace {
   __nv_bfloat16* images = nullptr;
-  float *nf32 = nullptr, *ef32 = nullptr;
+  float* nf32 = nullptr;
   std::vector<__nv_bfloat16*> nf16, ef16, agg16;
   std::vector<MlpSave> saves;
   size_t bytes = 0;
@@ -58,7 +62,6 @@ void tc_layout(const mgn_model* m, const mgn_graph* g, bool training, void* base
   Bump b(base);
   w.images = static_cast<__nv_bfloat16*>(b.raw((size_t)m->images->n_tiles * kTileB));
   w.nf32 = b.f((size_t)N * 128);
-  w.ef32 = b.f((size_t)std::max<int64_t>(E, 1) * 128);
   const int nlat = training ? mps + 1 : 1;
   w.nf16.resize(nlat);
   w.ef16.resize(nlat);
@@ -108,7 +111,8 @@ void fill_layers(const mgn_model* m, size_t mi, const float* params, const TcWor
 
 // Scratch of the backward pass, placed after the forward workspace.
 struct BwdScratch {
-  float *d_nf = nullptr, *d_ef = nullptr, *d_agg = nullptr;  // fp32 gradients of the latents
+  float *d_nf = nullptr, *d_agg = nullptr;                   // fp32 gradients of the node latent / the aggregate
+  __nv_bfloat16* d_ef = nullptr;                             // gradient of the edge latent: bf16 tile images (as the latent)
   __nv_bfloat16* dxs = nullptr;                              // sender adjoint rows as tile images [edge tile][2][16 KB]
   __nv_bfloat16 *dz0 = nullptr, *ztop = nullptr;             // tile images
   // weight-gradient partials of ONE MLP at a time: chain kernel (per CTA), input kernel (per CTA), CUDA-core helper
@@ -118,12 +122,12 @@ struct BwdScratch {
 };
 
 void bwd_layout(const mgn_model* m, const mgn_graph* g, void* base, BwdScratch& b) {
-  const int64_t N = g->N, E = g->E;
+  const int64_t N = g->N;
   const int64_t node_tiles = (N + kTile - 1) / kTile, edge_tiles = g->n_edge_tiles;
   const int64_t max_tiles = std::max<int64_t>(std::max(node_tiles, edge_tiles), 1);
   Bump bump(base);
   b.d_nf = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
-  b.d_ef = bump.f((size_t)std::max<int64_t>(E, 1) * 128);
+  b.d_ef = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(edge_tiles, 1) * 2 * kTileB));
   b.d_agg = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
   b.dxs = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(edge_tiles, 1) * 2 * kTileB));  // tile images
   b.dz0 = static_cast<__nv_bfloat16*>(bump.raw((size_t)max_tiles * 2 * kTileB));
@@ -239,7 +243,6 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.raw_F = m->cfg.edge_in;
       p.ksteps0 = (m->cfg.edge_in + 15) / 16;
       p.fin_mode = FIN_LN;
-      p.lat_out = w.ef32;
       p.lat_img_out = w.ef16[0];
       MGN_CUDA_TRY(mlp_forward_tc(p, st));
     }
@@ -263,8 +266,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.idx1 = g->recv_csr;
       p.fin_mode = FIN_LN_RESID_AGG;
       if (k + 1 < mps) {  // the edge latent after the last MP step is never read (the decoder takes the nodes only)
-        p.lat_in = w.ef32;
-        p.lat_out = w.ef32;
+        p.lat_img_in = w.ef16[cur];   // residual = the bf16 latent itself (in place when not training: tile-local)
         p.lat_img_out = w.ef16[nxt];
       }
       p.agg_bf16 = agg;
@@ -331,7 +333,7 @@ struct BwdCtx {
 // Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
 // LayerNorm (dy = dy_a[r] + dy_b[b_idx[r]]); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
 int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const float* dy_b,
-                  const int32_t* b_idx, Pieces& pc) {
+                  const int32_t* b_idx, Pieces& pc, const __nv_bfloat16* dy_a_img = nullptr) {
   const MlpLayout& L = c.m->mlps[mi];
   const MlpImages& im = c.m->images->mlps[mi];
   const MlpSave& sv = c.w->saves[mi];
@@ -344,6 +346,7 @@ int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a,
   if (L.layer_norm) {
     p.head_mode = HEAD_LN;
     p.dy_a = dy_a;
+    p.dy_a_img = dy_a_img;
     p.dy_b = dy_b;
     p.b_idx = b_idx;
     p.xhat = sv.xhat;
@@ -474,7 +477,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     if (E > 0) {  // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
       const size_t mi = 2 + 2 * k;
       Pieces pc{};
-      MGN_TRY(run_chain(c, mi, true, d_ef_valid ? b.d_ef : nullptr, b.d_agg, g->recv_csr, pc));
+      MGN_TRY(run_chain(c, mi, true, nullptr, b.d_agg, g->recv_csr, pc, d_ef_valid ? b.d_ef : nullptr));
       InputParams p{};
       p.n_tiles = g->n_edge_tiles;
       p.M = E;
@@ -492,9 +495,9 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.bf16_dst[0] = b.dxs;
       p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores into the buffer that
       p.f32_dst[1] = b.d_agg;       // held d_agg (consumed by the chain kernel above), added to d_nf by the gather below
-      p.sink[2] = SINK_ADD_F32;     // edge-latent residual
-      p.f32_src[2] = d_ef_valid ? b.d_ef : nullptr;
-      p.f32_dst[2] = b.d_ef;
+      p.sink[2] = SINK_ADD_IMG;     // edge-latent residual: d_ef = bf16(d_ef + dX), tile images, in place
+      p.img_src[2] = d_ef_valid ? b.d_ef : nullptr;
+      p.bf16_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p, pc));
       MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st));
     } else {  // no edges: the edge MLP of this step has a zero gradient
@@ -507,7 +510,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     const MlpLayout& L = m->mlps[1];
     if (mps > 0 && E > 0) {
       Pieces pc{};
-      MGN_TRY(run_chain(c, 1, true, b.d_ef, nullptr, nullptr, pc));
+      MGN_TRY(run_chain(c, 1, true, nullptr, nullptr, nullptr, pc, b.d_ef));
       MGN_TRY(run_encoder_input(c, 1, true, io ? io->edge : identity_recipe(ef, m->cfg.edge_in), g->perm, nullptr, pc));
     } else {
       const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];

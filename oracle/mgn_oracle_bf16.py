@@ -1,7 +1,7 @@
 """CPU model of the product's MGN_COMPUTE_BF16 arithmetic (tcgen05 path): the SAME algorithm as
 oracle/mgn_oracle.py (which restates the reference), with a round-to-nearest-even to bfloat16
 inserted at exactly the points where the CUDA kernels store a bf16 value (GEMM operands, saved
-activations, staged gradient tiles).  Accumulation is exact (float64) where the kernels accumulate
+activations, staged gradient tiles, and the edge latent / its gradient, which have no fp32 master copy).  Accumulation is exact (float64) where the kernels accumulate
 in fp32.
 
 TEST INFRASTRUCTURE ONLY (same rule as mgn_oracle.py).  Purpose: split the bf16-mode parity claim
@@ -144,13 +144,13 @@ def step_bf16(cfg: orc.ModelConfig, params, nf, ef, senders, receivers, target, 
 
     enc_n, enc_e = mk(0), mk(1)
     nf32 = enc_n.forward(q(nf))
-    ef32 = enc_e.forward(q(np.asarray(ef)[perm]))
-    nf16, ef16 = [q(nf32)], [q(ef32)]
+    ef32 = q(enc_e.forward(q(np.asarray(ef)[perm])))   # the edge latent is STORED in bf16 only (no fp32 master)
+    nf16, ef16 = [q(nf32)], [ef32]
     agg16, edges, nodes = [], [], []
     for k in range(cfg.mps):
         me, mn = mk(2 + 2 * k), mk(3 + 2 * k)
         m = me.forward(np.concatenate([nf16[k][sc_], nf16[k][rc_], ef16[k]], axis=1))
-        ef32 = f32(ef32 + m)
+        ef32 = q(ef32 + m)                             # residual on the bf16 latent, rounded once
         agg = q(_seg_sum(m, range(E), rc_, N))
         n = mn.forward(np.concatenate([nf16[k], agg], axis=1))
         nf32 = f32(nf32 + n)
@@ -192,7 +192,7 @@ def step_bf16(cfg: orc.ModelConfig, params, nf, ef, senders, receivers, target, 
         z0 = me.chain(g, me.head_ln(g, dy), L - 1)
         dx = me.input_dx(g, z0)
         recv = _seg_sum(dx[:, 128:256], range(E), rc_, N)       # tile-local segmented sum, stored ...
-        d_ef = f32(dx[:, 256:]) if d_ef is None else f32(d_ef + dx[:, 256:])
+        d_ef = dx[:, 256:] if d_ef is None else q(d_ef + dx[:, 256:])   # gradient of the edge latent: bf16 images too
         d_nf = _seg_sum(dx[:, :128], csc, sc_, N, init=f32(d_nf + recv))   # ... then added with the sender rows
     d_raw = None
     for enc, dy, raw in ((enc_e, d_ef, np.asarray(ef)[perm]), (enc_n, d_nf, nf)):
