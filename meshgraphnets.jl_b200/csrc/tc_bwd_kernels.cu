@@ -57,6 +57,9 @@ constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
 constexpr uint32_t kSmemTotal = kSmemTmem + 16;
 constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;
 
+// kDyImg: the fp32 part of dy comes as bf16 tile images (edge MLPs) - kept as raw bits until it is consumed, which frees
+// 16 registers of the head's double-buffered loads compared with the fp32 row-major form (node MLPs, encoders).
+template <bool kDyImg>
 __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -351,34 +354,34 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         const int* idx_c = idx_s + (t_local & 1) * kTile;
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L0: tile start
         const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
+        const uint8_t* dimg = reinterpret_cast<const uint8_t*>(p.dy_a_img) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint32_t zb = z_slot(zs) + (cc >> 3) * kTileB;
         // Four batches of 32 rows (2 per thread: i = 32 b + 2 rg + u), double buffered: the 14 loads of batch b + 1
         // (7 x 16 B per row) are in flight while batch b is computed, so the memory pipe never drains between batches.
-        float4 a0[4], a1[4], c0[4], c1[4];  // [buffer h][row u] at 2 h + u
+        float4 a0[kDyImg ? 1 : 4], a1[kDyImg ? 1 : 4], c0[4], c1[4];  // [buffer h][row u] at 2 h + u
+        uint4 aq[kDyImg ? 4 : 1];
         uint4 xq[4];
         float rs[4];
         auto issue = [&](int b, int h) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = 32 * b + rg * 2 + u, k = 2 * h + u;
-            a0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            a1[k] = a0[k];
-            c0[k] = a0[k];
-            c1[k] = a0[k];
+            if constexpr (kDyImg) aq[k] = make_uint4(0u, 0u, 0u, 0u);
+            else {
+              a0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+              a1[k] = a0[k];
+            }
+            c0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            c1[k] = c0[k];
             xq[k] = make_uint4(0u, 0u, 0u, 0u);
             rs[k] = 0.f;
             if (i < cnt) {
               const int64_t r = row0 + i;
-              if (p.dy_a) {
+              if constexpr (kDyImg) {  // 8 bf16 of the tile's own gradient image (same offset as the xhat chunk below)
+                if (p.dy_a_img) aq[k] = *reinterpret_cast<const uint4*>(dimg + t128_off(i, cc & 7));
+              } else if (p.dy_a) {
                 a0[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
                 a1[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
-              } else if (p.dy_a_img) {  // 8 bf16 of the tile's own gradient image
-                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.dy_a_img) + (size_t)tile * kImg +
-                                                                (cc >> 3) * kTileB + t128_off(i, cc & 7));
-                a0[k] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
-                                    __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
-                a1[k] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u),
-                                    __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
               }
               if (p.dy_b) {
                 // consecutive CSR rows share their receiver: reuse the previous row's gather instead of asking L2
@@ -401,8 +404,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = 32 * b + rg * 2 + u, k = 2 * h + u;
-            const float dy[8] = {a0[k].x + c0[k].x, a0[k].y + c0[k].y, a0[k].z + c0[k].z, a0[k].w + c0[k].w,
-                                 a1[k].x + c1[k].x, a1[k].y + c1[k].y, a1[k].z + c1[k].z, a1[k].w + c1[k].w};
+            float dy[8];
+            if constexpr (kDyImg) {
+              const uint32_t aw[4] = {aq[k].x, aq[k].y, aq[k].z, aq[k].w};
+              const float cv[8] = {c0[k].x, c0[k].y, c0[k].z, c0[k].w, c1[k].x, c1[k].y, c1[k].z, c1[k].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                dy[2 * e] = __uint_as_float(aw[e] << 16) + cv[2 * e];
+                dy[2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + cv[2 * e + 1];
+              }
+            } else {
+              dy[0] = a0[k].x + c0[k].x; dy[1] = a0[k].y + c0[k].y; dy[2] = a0[k].z + c0[k].z; dy[3] = a0[k].w + c0[k].w;
+              dy[4] = a1[k].x + c1[k].x; dy[5] = a1[k].y + c1[k].y; dy[6] = a1[k].z + c1[k].z; dy[7] = a1[k].w + c1[k].w;
+            }
             const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
             float xh[8];
 #pragma unroll
@@ -1134,8 +1148,12 @@ unsigned long long* take_trace(int) { return nullptr; }
 cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStream_t st) {
   static PerDeviceOnce configured;
   cudaError_t ce = configured.run([](int) {
-    return cudaFuncSetAttribute(chain::mlp_bwd_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)chain::kSmemLaunch);
+    cudaError_t e = cudaFuncSetAttribute(chain::mlp_bwd_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)chain::kSmemLaunch);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(chain::mlp_bwd_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)chain::kSmemLaunch);
+    return e;
   });
   if (ce != cudaSuccess) return ce;
   const int grid = backward_grid(p.n_tiles);
@@ -1144,7 +1162,10 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
   ProfScope ps(TAG_TC_MLP_BWD, st);
   ChainParams q = p;
   q.trace = take_trace(1);
-  chain::mlp_bwd_chain_kernel<<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(q);
+  if (q.dy_a == nullptr && q.head_mode == HEAD_LN)   // image form (or no fp32 part at all: the last MP step's edge MLP)
+    chain::mlp_bwd_chain_kernel<true><<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(q);
+  else
+    chain::mlp_bwd_chain_kernel<false><<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(q);
   return cudaGetLastError();
 }
 
