@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--no-partition-leg", action="store_true",
                     help="N > 1: skip the graph-partitioned (BASELINE configs[4]) extra measurement")
     ap.add_argument("--partition-edges-per-rank", type=float, default=3.4e6)
+    ap.add_argument("--no-shooting-leg", action="store_true",
+                    help="skip the interval-sharded MultipleShooting extra measurement (strong scaling over N)")
     return ap.parse_args()
 
 
@@ -394,6 +396,13 @@ def run_ours(args, rank, world, local_rank):
             leg = {"error": repr(e)}
         if line is not None:
             line["partitioned_mesh"] = leg
+    if not args.no_shooting_leg:
+        try:
+            leg = shooting_leg(args, pkg, rank, world, local_rank, extras if isinstance(extras, pkg.Communicator) else None)
+        except Exception as e:
+            leg = {"error": repr(e)}
+        if line is not None:
+            line["multiple_shooting_sharded"] = leg
     if world == 1 and args.batch != 1:
         # the reference's own granularity: ONE window per step (batchsize is "not implemented yet",
         # src/MeshGraphNets.jl:224) - a latency number, reported beside the throughput headline
@@ -465,15 +474,40 @@ def partition_leg(args, pkg, rank, world, local_rank, comm):
         loss = step(timed_exchange)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / K
+    ms_eager = e0.elapsed_time(e1) / K
     ex_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    # the same step - 33 stages, 29 halo exchanges, 2 all-reduces - captured once and replayed as ONE CUDA graph
+    ms, captured = ms_eager, False
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step(base)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss_g = step(base)
+        graph.replay()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(K):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms, captured, loss = e0.elapsed_time(e1) / K, True, loss_g
+    except Exception as e:       # capture not possible on this stack: the eager number stands
+        print(f"[bench] partitioned step: CUDA graph capture failed ({e!r}); eager launches", file=sys.stderr)
+        torch.cuda.synchronize()
     halo = sum(len(v) for v in part.recv_rows.values())
-    tt = torch.tensor([ms, ex_ms, float(halo), float(len(part.edge_ids))], device=dev, dtype=torch.float64)
+    tt = torch.tensor([ms, ex_ms, float(halo), float(len(part.edge_ids)), ms_eager], device=dev, dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ws_gb = model.workspace_bytes(pm.graph.index, True) / 1e9
     lat_b, grad_b = model.halo_row_bytes(pkg.HALO_LATENT), model.halo_row_bytes(pkg.HALO_GRAD)
     return {"workload": f"kuhn_tet_grid_{n}^3_partitioned_train_step", "nodes": N, "edges": E, "mps": MPS,
             "ms_per_step": float(tt[0]), "mp_step_edges_per_sec": E * MPS / (float(tt[0]) * 1e-3),
+            "cuda_graph": captured, "ms_per_step_eager": float(tt[4]),
             "exchange_ms_per_step_max_rank": float(tt[1]), "exchanges_per_step": 2 * MPS - 1,
             "halo_rows_max_rank": int(tt[2]), "edges_max_rank": int(tt[3]),
             "halo_bytes_per_step_max_rank": int(tt[2]) * ((MPS - 1) * lat_b + MPS * grad_b),
@@ -481,6 +515,70 @@ def partition_leg(args, pkg, rank, world, local_rank, comm):
             "transport": "mgn_halo_exchange (library NCCL, grouped send/recv on the compute stream)" if comm is not None
                          else "torch.distributed all_to_all_single",
             "final_loss": float(loss.cpu())}
+
+
+def shooting_leg(args, pkg, rank, world, local_rank, comm):
+    """SURVEY 8e row 4 on the driver's record: one MultipleShooting training step (src/strategies.jl:310-386) over a
+    200-observation CylinderFlow trajectory = 40 shooting intervals (interval_size 6, Euler, 15 MP steps), the intervals
+    sharded over the ranks (rank r integrates intervals r, r + world, ... in lock-step as one block-diagonal graph),
+    loss and gradient SUM-all-reduced.  Strong scaling: the work is fixed, so `ms_per_step` falls with N."""
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    T = 200
+    pos, cells, nt = pkg.cylinder_flow_mesh(NX, NY)
+    vel = pkg.synthetic_velocity(pos, T + 1, seed=1)
+    data_h = {"node_type": nt.reshape(1, -1, 1), "mesh_pos": pos[None], "cells": cells[None]}
+    node_type, senders, receivers, ef = pkg.create_base_graph(data_h, 6, 0, device=dev)
+    mode = pkg.COMPUTE_BF16 if args.mode == "bf16" else pkg.COMPUTE_FP32
+    model, ps, st = pkg.build_model(9, 2, 2, MPS, LATENT, HIDDEN, device=dev, compute_mode=mode)
+    mgn = pkg.GraphNetwork(model, ps, st, pkg.NormaliserOnline(3, dev),
+                           {"velocity": pkg.NormaliserOnline(2, dev), "node_type": pkg.NormaliserOfflineMinMax(0.0, 1.0)},
+                           {"velocity": pkg.NormaliserOnline(2, dev)})
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    data = {"velocity": to(vel[:T]), "target|velocity": to(vel[1:T + 1]),
+            "node_type": to(nt.reshape(1, -1, 1).astype(np.int32))}
+    for f in range(3):
+        mgn.n_norm["velocity"](data["velocity"][f])
+        mgn.o_norm["velocity"]((data["velocity"][f + 1] - data["velocity"][f]) / 0.01)
+    mgn.e_norm(ef)
+    meta = {"dt": 0.01, "features": {"velocity": {"dim": 2}}, "target_features": ["velocity"]}
+    vm = to(pkg.val_mask(nt, [0, 5], 2))
+    t = (mgn, data, meta, ["velocity"], ["velocity"], node_type, ef, senders, receivers, 1, None, vm)
+    n_int = len(pkg.shooting_ranges(T, 6))
+    strat = pkg.MultipleShooting(0.0, 0.01, 0.01 * (T - 1), "euler", interval_size=6, continuity_term=100, rank=rank,
+                                 world=world)
+    tt = pkg.init_train_step(strat, t, None)
+
+    def step():
+        (gs,), loss = pkg.train_step(strat, tt)
+        if world > 1:
+            if comm is not None:
+                comm.allreduce_sum_(gs); comm.allreduce_sum_(loss)
+            else:
+                pkg.allreduce_sum_(gs, loss)
+        return gs, loss
+
+    step()
+    times = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gs, loss = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times.append(float(ms.cpu()))
+    ms = float(np.median(times))
+    E = int(senders.shape[0])
+    return {"workload": "cylinder_flow_multiple_shooting_step_intervals_sharded", "observations": T, "intervals": n_int,
+            "intervals_per_rank": len(pkg.shard_intervals(n_int, 0, world)), "solver": "euler", "scaling": "strong",
+            "ms_per_step": ms, "mp_step_edges_per_sec_train_equiv": (5 + 5 / 3) * n_int * E * MPS / (ms * 1e-3),
+            "loss": float(loss.cpu()), "grad_norm": float(gs.norm().cpu())}
 
 
 def extra_measurements(args, pkg, model, mgn, E, B, dev, step_fn, n_nodes):

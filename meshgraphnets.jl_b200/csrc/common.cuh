@@ -6,6 +6,7 @@
 #include <stddef.h>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/mgn_b200.h"
@@ -70,8 +71,36 @@ struct TuneKnobs {
   int fwd_epi_warps = 8;   // MGN_FWD_EPI_WARPS=4 selects the one-thread-per-row epilogue
   int fwd_stagger_ns = 0;  // MGN_FWD_STAGGER_NS
   int fwd_deep_ring = 1;   // MGN_FWD_DEEP_RING=0 disables the deep-ring variant for small graphs
+  int pdl = 0;             // MGN_PDL=1: programmatic dependent launch between the library's kernels (measured: no gain
+                           // inside a CUDA graph, -3 % on the 32-window step; kept as an opt-in for eager callers)
 };
 TuneKnobs read_tune_knobs();
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------------
+// Consecutive kernels of a forward / backward pass are launched with programmatic stream serialization: a kernel's CTAs
+// may become resident (and run their prologue: barrier init, TMEM allocation) while the previous kernel drains; every
+// kernel executes pdl_wait() BEFORE its first global-memory access (read or write), which returns only when the whole
+// previous grid has completed and its writes are visible - so the data dependencies are exactly those of plain
+// launches.  pdl_trigger() at the top of a kernel lets its successor be scheduled as soon as SM resources free up.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+cudaError_t launch_kernel(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 constexpr int kMaxDense = 8;
 constexpr int kOdeMaxTerms = 8;  // terms of one explicit Runge-Kutta combination (mgn_ode_lincomb)

@@ -60,7 +60,7 @@ struct ModelImages {
   int n_tiles = 0;
 };
 
-cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat16* images, cudaStream_t st);
+cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat16* images, cudaStream_t st, bool pdl);
 
 // ---- fused MLP forward -----------------------------------------------------------------------------
 enum InMode { IN_RAW = 0, IN_PLAIN = 1, IN_CONCAT2 = 2, IN_GATHER3 = 3 };
@@ -110,6 +110,7 @@ struct FwdParams {
   uint32_t stagger_ns;                    // start delay unit that de-phases co-resident CTAs (0 = off)
   int epi_warps;                          // 8 (two threads per tile row) or 4: mgn_model::knobs
   int deep_ring;                          // allow the deep-ring variant when the graph has no more tiles than SMs
+  int pdl;                                // programmatic dependent launch (common.cuh)
 };
 
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st);
@@ -148,6 +149,7 @@ struct ChainParams {
   __nv_bfloat16* dz_out;               // image of the last dZ
   float* partial;                      // [grid][chain_partial_floats(nsteps)]
   unsigned long long* trace;           // debug (see FwdParams::trace)
+  int pdl;
 };
 // per-CTA partial layout: dW[j] at j*16384 ; db[i] at nsteps*16384 + i*128 (i = 0: top dZ, i = j+1: dZ
 // produced by step j) ; g_scale, g_bias after the db block.
@@ -179,6 +181,7 @@ struct InputParams {
   const __nv_bfloat16* img_src[3];     // SINK_ADD_IMG
   float* partial;                      // [grid][nblk * 16384]
   unsigned long long* trace;           // debug (see FwdParams::trace)
+  int pdl;
 };
 cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st);
 
@@ -188,24 +191,24 @@ constexpr int kMaxPieces = 12;
 struct Pieces { Piece p[kMaxPieces]; int n; };
 // For every piece: dst[i] = sum_k src[k * stride + i], k < n_parts   (fixed order: deterministic).  One launch reduces
 // the partials of all kernels of one MLP (chain + input layer, or decoder head + chain + input layer).
-cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st);
+cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st, bool pdl);
 // Decoder head: dZ_{L-2} = (dout W_{L-1}^T) .* (H_{L-2} > 0) as an image, plus per-tile partials of
 // dW_{L-1} [128][od], db_{L-1} [od] and db_{L-2} [128]  (stride 128*od + od + 128 floats per tile).
 // out_feat / val_mask: the cotangent is first pulled back through `inverse_data(...) .* val_mask` (fused output).
 cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,
                              int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, const FeatRecipe& out_feat,
-                             const float* val_mask, cudaStream_t st);
+                             const float* val_mask, cudaStream_t st, bool pdl);
 // Encoder input layer: dW_0 [F][128] per-tile partials from the dZ_0 image and the raw fp32 features;
 // d_raw [rows][F] = dZ_0 W_0^T when requested.
 // raw features come from a recipe; d_raw is the gradient w.r.t. the recipe's SOURCE columns (transposed normaliser applied).
 cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const FeatRecipe& feat, const int32_t* raw_idx, int F,
                               const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
-                              float* partial, float* d_raw, cudaStream_t st);
+                              float* partial, float* d_raw, cudaStream_t st, bool pdl);
 // d_nf[v] += recv_sum[v] + sum over CSC row v of dxs[csc_slot[j]]  (adjoints of the receiver and sender gathers;
 // recv_sum is the tile-local segmented sum the input kernel stored; fixed order: deterministic)
 // dxs is a tile-image tensor; csc_pos maps a CSC entry to its row in image space (tile * 128 + row in tile).
 cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs_img, const int32_t* col_ptr,
-                              const int32_t* csc_pos, int64_t N, cudaStream_t st);
+                              const int32_t* csc_pos, int64_t N, cudaStream_t st, bool pdl);
 
 }  // namespace tc
 }  // namespace mgn

@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   const int ns = p.nsteps;
   float* my_partial = p.partial + (size_t)blockIdx.x * chain_partial_floats(ns);
 
-  if (p.head_mode == HEAD_LN)
-    for (int i = tid; i < 128; i += kThreads) scale_s[i] = p.ln_scale[i];
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
   if (tid == 0) {
     for (int s = 0; s < kZ; ++s) {
       mbar_init(z_full(s), 1);
@@ -105,6 +104,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     fence_mbar_init();
   }
   if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 512);
+  pdl_wait();      // no global memory access above this line
+  if (p.head_mode == HEAD_LN)
+    for (int i = tid; i < 128; i += kThreads) scale_s[i] = p.ln_scale[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -560,6 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
   const int nblk = p.nblk;
   float* my_partial = p.partial + (size_t)blockIdx.x * (size_t)nblk * 16384;
 
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kZ; ++s) {
       mbar_init(z_full(s), 1);
@@ -579,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     fence_mbar_init();
   }
   if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 512);
+  pdl_wait();      // no global memory access above this line
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -892,6 +896,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
 // Block = 32 outputs x 8 part groups: thread (x, y) sums parts y, y+8, ... of output x (coalesced across x),
 // then the 8 group sums are added in a fixed order -> deterministic, 8x the memory parallelism of a plain loop.
 __global__ void __launch_bounds__(256) reduce_pieces_kernel(const Pieces pieces, int64_t total) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + x;
@@ -921,6 +927,8 @@ __global__ void __launch_bounds__(256) reduce_pieces_kernel(const Pieces pieces,
 // strides that are multiples of 4 - all pieces but the decoder's last layer.  Per output the parts are added in exactly
 // the order of the scalar kernel (parts y, y+8, ... then the 8 groups), so both kernels give the same bits.
 __global__ void __launch_bounds__(256) reduce_pieces4_kernel(const Pieces pieces, int64_t total4) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 red[8][33];
   const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * 32 + x;
@@ -972,6 +980,8 @@ __global__ void __launch_bounds__(128) decoder_head_kernel(const float* __restri
                                                            const float* __restrict__ val_mask) {
   __shared__ float dout_s[128 * 16];
   __shared__ FeatCol otab[16];
+  pdl_trigger();
+  pdl_wait();
   const int tile = blockIdx.x, c = threadIdx.x;
   const int64_t row0 = (int64_t)tile * kTile;
   const int cnt = (int)min((int64_t)kTile, M - row0);
@@ -1042,6 +1052,8 @@ __global__ void __launch_bounds__(128) encoder_input_kernel(const __nv_bfloat16*
   float* x_s = es + 128 * 129;   // [128][F]
   __shared__ FeatCol ftab[kMaxFeat];
   const int tile = blockIdx.x, t = threadIdx.x;
+  pdl_trigger();
+  pdl_wait();
   feat_table(feat, ftab, t, 128);
   int64_t row0;
   int cnt;
@@ -1095,6 +1107,8 @@ __global__ void __launch_bounds__(256) sender_gather_add_kernel(float* __restric
                                                                 const __nv_bfloat16* __restrict__ dxs_img,
                                                                 const int32_t* __restrict__ col_ptr,
                                                                 const int32_t* __restrict__ csc_pos, int64_t N) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (v >= N) return;
   const int lane = threadIdx.x & 31;
@@ -1163,10 +1177,8 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
   ChainParams q = p;
   q.trace = take_trace(1);
   if (q.dy_a == nullptr && q.head_mode == HEAD_LN)   // image form (or no fp32 part at all: the last MP step's edge MLP)
-    chain::mlp_bwd_chain_kernel<true><<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(q);
-  else
-    chain::mlp_bwd_chain_kernel<false><<<grid, chain::kThreads, chain::kSmemLaunch, st>>>(q);
-  return cudaGetLastError();
+    return launch_kernel(p.pdl != 0, chain::mlp_bwd_chain_kernel<true>, dim3(grid), dim3(chain::kThreads), chain::kSmemLaunch, st, q);
+  return launch_kernel(p.pdl != 0, chain::mlp_bwd_chain_kernel<false>, dim3(grid), dim3(chain::kThreads), chain::kSmemLaunch, st, q);
 }
 
 cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStream_t st) {
@@ -1182,11 +1194,10 @@ cudaError_t mlp_backward_input_tc(const InputParams& p, int* grid_out, cudaStrea
   ProfScope ps(TAG_TC_DW, st);
   InputParams q = p;
   q.trace = take_trace(2);
-  input::mlp_bwd_input_kernel<<<grid, input::kThreads, input::kSmemLaunch, st>>>(q);
-  return cudaGetLastError();
+  return launch_kernel(p.pdl != 0, input::mlp_bwd_input_kernel, dim3(grid), dim3(input::kThreads), input::kSmemLaunch, st, q);
 }
 
-cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st) {
+cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st, bool pdl) {
   int64_t total = 0;
   for (int i = 0; i < pieces.n; ++i) total += pieces.p[i].count;
   if (total == 0) return cudaSuccess;
@@ -1197,23 +1208,22 @@ cudaError_t reduce_pieces(const Pieces& pieces, cudaStream_t st) {
           (reinterpret_cast<uintptr_t>(q.dst) & 15) == 0;
   }
   ProfScope ps(TAG_REDUCE_PARTIALS, st);
-  if (vec) reduce_pieces4_kernel<<<(unsigned)((total / 4 + 31) / 32), 256, 0, st>>>(pieces, total / 4);
-  else reduce_pieces_kernel<<<(unsigned)((total + 31) / 32), 256, 0, st>>>(pieces, total);
-  return cudaGetLastError();
+  if (vec) return launch_kernel(pdl, reduce_pieces4_kernel, dim3((unsigned)((total / 4 + 31) / 32)), dim3(256), 0, st, pieces, total / 4);
+  return launch_kernel(pdl, reduce_pieces_kernel, dim3((unsigned)((total + 31) / 32)), dim3(256), 0, st, pieces, total);
 }
 
 cudaError_t decoder_head_bwd(const float* dout, int out_dim, const float* w_last, const __nv_bfloat16* h_img,
                              int n_tiles, int64_t M, __nv_bfloat16* z_img, float* partial, const FeatRecipe& out_feat,
-                             const float* val_mask, cudaStream_t st) {
+                             const float* val_mask, cudaStream_t st, bool pdl) {
   if (n_tiles == 0) return cudaSuccess;
   ProfScope ps(TAG_TC_MISC, st);
-  decoder_head_kernel<<<n_tiles, 128, 0, st>>>(dout, out_dim, w_last, h_img, M, z_img, partial, out_feat, val_mask);
-  return cudaGetLastError();
+  return launch_kernel(pdl, decoder_head_kernel, dim3(n_tiles), dim3(128), 0, st, dout, out_dim, w_last, h_img, M, z_img, partial,
+                       out_feat, val_mask);
 }
 
 cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const FeatRecipe& feat, const int32_t* raw_idx, int F,
                               const float* w0, int n_tiles, int64_t M, const int32_t* tile_row_start,
-                              float* partial, float* d_raw, cudaStream_t st) {
+                              float* partial, float* d_raw, cudaStream_t st, bool pdl) {
   if (n_tiles == 0) return cudaSuccess;
   const size_t smem = (size_t)(128 * 129 + 128 * F) * sizeof(float);
   static PerDeviceOnce configured;
@@ -1223,16 +1233,16 @@ cudaError_t encoder_input_bwd(const __nv_bfloat16* dz0, const FeatRecipe& feat, 
   });
   if (ce != cudaSuccess) return ce;
   ProfScope ps(TAG_TC_MISC, st);
-  encoder_input_kernel<<<n_tiles, 128, smem, st>>>(dz0, feat, raw_idx, F, w0, M, tile_row_start, partial, d_raw);
-  return cudaGetLastError();
+  return launch_kernel(pdl, encoder_input_kernel, dim3(n_tiles), dim3(128), smem, st, dz0, feat, raw_idx, F, w0, M, tile_row_start,
+                       partial, d_raw);
 }
 
 cudaError_t sender_gather_add(float* d_nf, const float* recv_sum, const __nv_bfloat16* dxs_img, const int32_t* col_ptr,
-                              const int32_t* csc_pos, int64_t N, cudaStream_t st) {
+                              const int32_t* csc_pos, int64_t N, cudaStream_t st, bool pdl) {
   if (N == 0) return cudaSuccess;
   ProfScope ps(TAG_NODE_GRAD_GATHER, st);
-  sender_gather_add_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(d_nf, recv_sum, dxs_img, col_ptr, csc_pos, N);
-  return cudaGetLastError();
+  return launch_kernel(pdl, sender_gather_add_kernel, dim3((unsigned)((N + 7) / 8)), dim3(256), 0, st, d_nf, recv_sum, dxs_img, col_ptr,
+                       csc_pos, N);
 }
 
 }  // namespace tc

@@ -51,6 +51,8 @@ constexpr int kRingShared = 4, kRingDeep = 10;
 __global__ void __launch_bounds__(256)
 pack_kernel(const PackTile* __restrict__ tiles, const float* __restrict__ params,
             __nv_bfloat16* __restrict__ images) {
+  pdl_trigger();
+  pdl_wait();
   const PackTile t = tiles[blockIdx.x];
   const float* W = params + t.w_off;  // [in][out] row-major
   uint8_t* dst = reinterpret_cast<uint8_t*>(images) + (size_t)blockIdx.x * kTileB;
@@ -127,17 +129,10 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
-  if (p.in_mode == IN_RAW) feat_table(p.feat, ftab, tid, kThreads);
-  if (p.fin_mode == FIN_LINEAR && p.out_feat.n > 0) feat_table(p.out_feat, otab, tid, kThreads);
 
-  // ---- one-time setup
-  for (int i = tid; i < L * 128; i += kThreads) {
-    const int l = i >> 7, c = i & 127;
-    const int nout = (l == L - 1) ? p.n_out_last : 128;
-    bias_s[i] = c < nout ? p.bias[l][c] : 0.f;
-  }
-  if (p.fin_mode != FIN_LINEAR)
-    for (int i = tid; i < 256; i += kThreads) ln_s[i] = i < 128 ? p.ln_scale[i] : p.ln_bias[i - 128];
+  // ---- one-time setup.  Everything that touches no global memory first (barriers, TMEM allocation): with programmatic
+  //      dependent launch this part overlaps the tail of the previous kernel; pdl_wait() then orders every global access.
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < kRing; ++s) {
       mbar_init(full_bar(s), 32 * NP);
@@ -148,6 +143,16 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
     fence_mbar_init();
   }
   if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 128);
+  pdl_wait();
+  if (p.in_mode == IN_RAW) feat_table(p.feat, ftab, tid, kThreads);
+  if (p.fin_mode == FIN_LINEAR && p.out_feat.n > 0) feat_table(p.out_feat, otab, tid, kThreads);
+  for (int i = tid; i < L * 128; i += kThreads) {
+    const int l = i >> 7, c = i & 127;
+    const int nout = (l == L - 1) ? p.n_out_last : 128;
+    bias_s[i] = c < nout ? p.bias[l][c] : 0.f;
+  }
+  if (p.fin_mode != FIN_LINEAR)
+    for (int i = tid; i < 256; i += kThreads) ln_s[i] = i < 128 ? p.ln_scale[i] : p.ln_bias[i - 128];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -574,11 +579,10 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
 
 }  // namespace
 
-cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat16* images, cudaStream_t st) {
+cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat16* images, cudaStream_t st, bool pdl) {
   if (im.n_tiles == 0) return cudaSuccess;
   ProfScope ps(TAG_TC_PACK, st);
-  pack_kernel<<<im.n_tiles, 256, 0, st>>>(im.d_tiles, params, images);
-  return cudaGetLastError();
+  return launch_kernel(pdl, pack_kernel, dim3(im.n_tiles), dim3(256), 0, st, im.d_tiles, params, images);
 }
 
 // Variant selection comes from the model handle (FwdParams::epi_warps / deep_ring / stagger_ns, frozen at
@@ -603,13 +607,12 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
   FwdParams q = p;
   q.trace = take_trace(0);
   if (grid <= n_sm) q.stagger_ns = 0u;
+  const bool pdl = p.pdl != 0;
   if (p.epi_warps == 4)
-    mlp_fwd_kernel<4, kRingShared, 1><<<grid, 32 * 6, Lay<kRingShared>::kLaunch, st>>>(q);
-  else if (p.deep_ring && p.n_tiles <= n_sm)
-    mlp_fwd_kernel<8, kRingDeep, 4><<<grid, 32 * 13, Lay<kRingDeep>::kLaunch, st>>>(q);
-  else
-    mlp_fwd_kernel<8, kRingShared, 1><<<grid, 32 * 10, Lay<kRingShared>::kLaunch, st>>>(q);
-  return cudaGetLastError();
+    return launch_kernel(pdl, mlp_fwd_kernel<4, kRingShared, 1>, dim3(grid), dim3(32 * 6), Lay<kRingShared>::kLaunch, st, q);
+  if (p.deep_ring && p.n_tiles <= n_sm)
+    return launch_kernel(pdl, mlp_fwd_kernel<8, kRingDeep, 4>, dim3(grid), dim3(32 * 13), Lay<kRingDeep>::kLaunch, st, q);
+  return launch_kernel(pdl, mlp_fwd_kernel<8, kRingShared, 1>, dim3(grid), dim3(32 * 10), Lay<kRingShared>::kLaunch, st, q);
 }
 
 }  // namespace tc

@@ -107,6 +107,7 @@ void fill_layers(const mgn_model* m, size_t mi, const float* params, const TcWor
   p.epi_warps = m->knobs.fwd_epi_warps;
   p.deep_ring = m->knobs.fwd_deep_ring;
   p.stagger_ns = (uint32_t)m->knobs.fwd_stagger_ns;
+  p.pdl = m->knobs.pdl;
 }
 
 // Scratch of the backward pass, placed after the forward workspace.
@@ -215,7 +216,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
   const bool all = stage == kStageAll;
 
   if (all || stage == MGN_STAGE_ENCODE) {
-    MGN_CUDA_TRY(pack_weights(*m->images, params, w.images, st));
+    MGN_CUDA_TRY(pack_weights(*m->images, params, w.images, st, m->knobs.pdl != 0));
     // Encoder (a9): raw fp32 features -> latent; edge features arrive in original order (perm gather)
     {
       FwdParams p{};
@@ -367,6 +368,7 @@ int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a,
   }
   p.dz_out = c.b->dz0;
   p.partial = c.b->partial_chain;
+  p.pdl = c.m->knobs.pdl;
   int grid = 0;
   MGN_CUDA_TRY(mlp_backward_chain_tc(p, &grid, c.st));
   const float* base = c.b->partial_chain;
@@ -391,10 +393,11 @@ int32_t run_input(const BwdCtx& c, size_t mi, InputParams& p, Pieces& pc) {
   p.dz0 = (L.layer_norm || L.n_dense > 2) ? c.b->dz0 : c.b->ztop;
   p.wt_img = c.w->images + (size_t)im.bwd_off[0] * (kTileB / 2);
   p.partial = c.b->partial_input;
+  p.pdl = c.m->knobs.pdl;
   int grid = 0;
   MGN_CUDA_TRY(mlp_backward_input_tc(p, &grid, c.st));
   pc.p[pc.n++] = {c.b->partial_input, (int64_t)p.nblk * 16384, grid, c.grads + L.w_off[0], (int64_t)p.nblk * 16384};
-  MGN_CUDA_TRY(reduce_pieces(pc, c.st));
+  MGN_CUDA_TRY(reduce_pieces(pc, c.st, c.m->knobs.pdl != 0));
   return MGN_OK;
 }
 
@@ -405,9 +408,9 @@ int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const Feat
   const int F = L.in[0];
   MGN_CUDA_TRY(encoder_input_bwd(c.b->dz0, raw, raw_idx, F, c.params + L.w_off[0], n_tiles,
                                  edge_rows ? c.g->E : c.g->N, edge_rows ? c.g->tile_row_start : nullptr,
-                                 c.b->partial_misc, d_raw, c.st));
+                                 c.b->partial_misc, d_raw, c.st, c.m->knobs.pdl != 0));
   pc.p[pc.n++] = {c.b->partial_misc, (int64_t)F * 128, n_tiles, c.grads + L.w_off[0], (int64_t)F * 128};
-  MGN_CUDA_TRY(reduce_pieces(pc, c.st));
+  MGN_CUDA_TRY(reduce_pieces(pc, c.st, c.m->knobs.pdl != 0));
   return MGN_OK;
 }
 
@@ -436,7 +439,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     const MlpLayout& L = m->mlps[di];
     FeatRecipe no_out{};
     MGN_CUDA_TRY(decoder_head_bwd(dout, od, params + L.w_off[nd - 1], w.saves[di].h[nd - 2], node_tiles, N, b.ztop,
-                                  b.partial_misc, io ? io->out : no_out, io ? io->val_mask : nullptr, st));
+                                  b.partial_misc, io ? io->out : no_out, io ? io->val_mask : nullptr, st, m->knobs.pdl != 0));
     Pieces pc{};
     const int64_t hs = (int64_t)128 * od + od + 128;
     pc.p[pc.n++] = {b.partial_misc, hs, node_tiles, dparams + L.w_off[nd - 1], (int64_t)128 * od};
@@ -499,7 +502,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.img_src[2] = d_ef_valid ? b.d_ef : nullptr;
       p.bf16_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p, pc));
-      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st));
+      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st, m->knobs.pdl != 0));
     } else {  // no edges: the edge MLP of this step has a zero gradient
       const int64_t lo = m->mlps[2 + 2 * k].w_off[0], hi = m->mlps[3 + 2 * k].w_off[0];
       MGN_CUDA_TRY(cudaMemsetAsync(dparams + lo, 0, sizeof(float) * (hi - lo), st));
