@@ -65,12 +65,21 @@ int device_sm_count();  // SMs of the current device (cached per device, thread-
 enum ScratchKind : int { SCRATCH_LOSS = 0, SCRATCH_NORM = 1, SCRATCH_NORM_MULTI = 2, SCRATCH_KINDS };
 cudaError_t stream_scratch(cudaStream_t st, int kind, size_t bytes, void** out);
 void release_device_state();  // frees every scratch buffer (mgn_library_release)
+// A second stream per device for work that may run BESIDE the main pass: the fixed-order reduction of the weight-gradient
+// partials of MLP i overlaps the backward kernels of MLP i-1 (tc_pipeline.cu).  fork / done are indexed by the partial
+// buffer set (double buffered); every user joins the lane back into its stream before returning (capturable fork/join).
+struct ReduceLane {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr}, join = nullptr;
+};
+ReduceLane* reduce_lane();    // of the current device; nullptr if it cannot be created
 
 // Tuning knobs, read from the environment ONCE per model handle (mgn_model_create), never on the launch path.
 struct TuneKnobs {
   int fwd_epi_warps = 8;   // MGN_FWD_EPI_WARPS=4 selects the one-thread-per-row epilogue
   int fwd_stagger_ns = 0;  // MGN_FWD_STAGGER_NS
   int fwd_deep_ring = 1;   // MGN_FWD_DEEP_RING=0 disables the deep-ring variant for small graphs
+  int reduce_lane = 1;     // MGN_REDUCE_LANE=0: reduce the weight-gradient partials inline on the caller's stream
   int pdl = 0;             // MGN_PDL=1: programmatic dependent launch between the library's kernels (measured: no gain
                            // inside a CUDA graph, -3 % on the 32-window step; kept as an opt-in for eager callers)
 };
@@ -267,7 +276,8 @@ struct FusedIo;  // features.cuh: build_graph / inverse_data recipes evaluated i
 // enqueued on the stream; MLPs finish in descending index order (decoder first), so mlp_done(mi) means that the flat
 // gradient range from MLP mi to the end is final on the stream (dp.cu buckets the all-reduce / Adam update on it).
 struct GradHook {
-  virtual int32_t mlp_done(size_t mi) = 0;
+  // `where`: the stream on which the gradient of MLP mi (and of every MLP after it) is final
+  virtual int32_t mlp_done(size_t mi, cudaStream_t where) = 0;
   virtual ~GradHook() = default;
 };
 int32_t workspace_bytes(const mgn_model* m, const mgn_graph* g, bool training, size_t* bytes);

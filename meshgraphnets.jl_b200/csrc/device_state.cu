@@ -70,11 +70,30 @@ void release_device_state() {
   cudaSetDevice(cur);
 }
 
+ReduceLane* reduce_lane() {
+  static PerDeviceOnce once;
+  static ReduceLane lanes[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+  cudaError_t e = once.run([&](int d) {
+    ReduceLane& L = lanes[d];
+    cudaError_t r = cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && r == cudaSuccess; ++i) {
+      r = cudaEventCreateWithFlags(&L.fork[i], cudaEventDisableTiming);
+      if (r == cudaSuccess) r = cudaEventCreateWithFlags(&L.done[i], cudaEventDisableTiming);
+    }
+    if (r == cudaSuccess) r = cudaEventCreateWithFlags(&L.join, cudaEventDisableTiming);
+    return r;
+  });
+  return e == cudaSuccess ? &lanes[dev] : nullptr;
+}
+
 TuneKnobs read_tune_knobs() {
   TuneKnobs k;
   if (const char* e = getenv("MGN_FWD_EPI_WARPS")) k.fwd_epi_warps = atoi(e) == 4 ? 4 : 8;
   if (const char* e = getenv("MGN_FWD_STAGGER_NS")) k.fwd_stagger_ns = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("MGN_FWD_DEEP_RING")) k.fwd_deep_ring = atoi(e) == 0 ? 0 : 1;
+  if (const char* e = getenv("MGN_REDUCE_LANE")) k.reduce_lane = atoi(e) == 0 ? 0 : 1;
   if (const char* e = getenv("MGN_PDL")) k.pdl = atoi(e) == 1 ? 1 : 0;
   return k;
 }

@@ -138,11 +138,11 @@ struct BucketHook : GradHook {
 
   int64_t mlp_begin(size_t mi) const { return mi < m->mlps.size() ? m->mlps[mi].w_off[0] : m->n_params; }
 
-  int32_t mlp_done(size_t mi) override {
+  int32_t mlp_done(size_t mi, cudaStream_t where) override {
     while (next_bucket >= 0 && mi <= bucket_lo[next_bucket]) {
       const int b = next_bucket--;
       const int64_t lo = mlp_begin(bucket_lo[b]), hi = mlp_begin(bucket_lo[b + 1]);
-      MGN_CUDA_TRY(cudaEventRecord(ev_ready[b], st));
+      MGN_CUDA_TRY(cudaEventRecord(ev_ready[b], where));
       MGN_CUDA_TRY(cudaStreamWaitEvent(side, ev_ready[b], 0));
       if (comm && comm->world > 1)
         MGN_NCCL_TRY(n, n->AllReduce(grads + lo, grads + lo, (size_t)(hi - lo), ncclFloat32, ncclAvg, comm->comm, side));
@@ -329,7 +329,7 @@ int32_t mgn_backward_dp(const mgn_model* m, const mgn_graph* g, float* d_params,
   h.bucket_lo.push_back(n_mlp);
   h.next_bucket = nb - 1;
   MGN_TRY(backward(m, g, d_params, d_nf, d_ef, d_dout, d_dparams, d_dnf, d_workspace, workspace_bytes, st, &h));
-  MGN_TRY(h.mlp_done(0));  // whatever is left (nothing, unless a path skipped a notification)
+  MGN_TRY(h.mlp_done(0, st));  // whatever is left (nothing, unless a path skipped a notification)
   MGN_CUDA_TRY(cudaEventRecord(ev_join, h.side));
   MGN_CUDA_TRY(cudaStreamWaitEvent(st, ev_join, 0));
   return MGN_OK;

@@ -250,7 +250,7 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
                        size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook, const FusedIo* io) {
   if (m->cfg.compute_mode == MGN_COMPUTE_BF16)
     return tc_backward_stage(m, g, params, nf, ef, dout, dparams, dnf, ws, ws_bytes, stage, st, hook, io);
-  auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi) : MGN_OK; };
+  auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi, st) : MGN_OK; };
   Workspace w;
   layout(m, g, true, ws, w);
   if (w.bytes > ws_bytes) return fail(MGN_ERR_WORKSPACE, "workspace too small for mgn_backward");

@@ -118,7 +118,9 @@ struct BwdScratch {
   __nv_bfloat16 *dz0 = nullptr, *ztop = nullptr;             // tile images
   // weight-gradient partials of ONE MLP at a time: chain kernel (per CTA), input kernel (per CTA), CUDA-core helper
   // (per tile: decoder head or encoder input layer) - three regions so that one launch reduces them all
-  float *partial_chain = nullptr, *partial_input = nullptr, *partial_misc = nullptr;
+  // double buffered (set = MLP counter & 1): the reduction of one MLP's partials runs on the reduce lane while the
+  // kernels of the next MLP already fill the other set
+  float *partial_chain[2] = {nullptr, nullptr}, *partial_input[2] = {nullptr, nullptr}, *partial_misc[2] = {nullptr, nullptr};
   size_t bytes = 0;
 };
 
@@ -134,11 +136,13 @@ void bwd_layout(const mgn_model* m, const mgn_graph* g, void* base, BwdScratch& 
   b.dz0 = static_cast<__nv_bfloat16*>(bump.raw((size_t)max_tiles * 2 * kTileB));
   b.ztop = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(node_tiles, 1) * 2 * kTileB));
   const int grid = backward_grid((int)max_tiles);
-  b.partial_chain = bump.f((size_t)grid * chain_partial_floats(kMaxSteps));
-  b.partial_input = bump.f((size_t)grid * 3 * 16384);
   const size_t enc_f = (size_t)std::max(m->cfg.node_in, m->cfg.edge_in) * 128;
-  b.partial_misc = bump.f(std::max((size_t)max_tiles * enc_f,
-                                   (size_t)node_tiles * (size_t)(128 * m->cfg.out_dim + m->cfg.out_dim + 128)));
+  for (int s = 0; s < 2; ++s) {
+    b.partial_chain[s] = bump.f((size_t)grid * chain_partial_floats(kMaxSteps));
+    b.partial_input[s] = bump.f((size_t)grid * 3 * 16384);
+    b.partial_misc[s] = bump.f(std::max((size_t)max_tiles * enc_f,
+                                        (size_t)node_tiles * (size_t)(128 * m->cfg.out_dim + m->cfg.out_dim + 128)));
+  }
   b.bytes = bump.off;
 }
 
@@ -329,7 +333,59 @@ struct BwdCtx {
   TcWorkspace* w;
   BwdScratch* b;
   cudaStream_t st;
+  ReduceLane* lane = nullptr;   // nullptr: reductions run inline on st
+  GradHook* hook = nullptr;
+  mutable int set = 0;          // partial buffer set of the MLP in flight
+  mutable int used[2] = {0, 0}; // lane->done[set] has been recorded in this call
+  mutable bool forked = false;  // the lane has work of this call: join it before returning
+  float* pchain() const { return b->partial_chain[set]; }
+  float* pinput() const { return b->partial_input[set]; }
+  float* pmisc() const { return b->partial_misc[set]; }
 };
+
+// Before the first kernel of an MLP writes into the current partial set: its previous reduction (two MLPs ago) must be done.
+int32_t begin_mlp(const BwdCtx& c) {
+  if (c.lane && c.used[c.set]) MGN_CUDA_TRY(cudaStreamWaitEvent(c.st, c.lane->done[c.set], 0));
+  return MGN_OK;
+}
+// The fixed-order reduction of every partial of MLP `mi` (gathered in pc): on the reduce lane, beside the next MLP's
+// kernels, or inline.  Then the gradient of MLP mi is final: notify the hook with the stream it is final on.
+int32_t finish_mlp(const BwdCtx& c, size_t mi, const Pieces& pc) {
+  cudaStream_t where = c.st;
+  if (c.lane) {
+    MGN_CUDA_TRY(cudaEventRecord(c.lane->fork[c.set], c.st));
+    MGN_CUDA_TRY(cudaStreamWaitEvent(c.lane->side, c.lane->fork[c.set], 0));
+    MGN_CUDA_TRY(reduce_pieces(pc, c.lane->side, false));
+    MGN_CUDA_TRY(cudaEventRecord(c.lane->done[c.set], c.lane->side));
+    c.used[c.set] = 1;
+    c.forked = true;
+    where = c.lane->side;
+  } else {
+    MGN_CUDA_TRY(reduce_pieces(pc, c.st, c.m->knobs.pdl != 0));
+  }
+  c.set ^= 1;
+  return c.hook ? c.hook->mlp_done(mi, where) : MGN_OK;
+}
+
+// An MLP whose gradient is identically zero (no edges): cleared on the stream the other gradients become final on.
+int32_t zero_mlp(const BwdCtx& c, size_t mi, int64_t lo, int64_t hi) {
+  cudaStream_t where = c.st;
+  if (c.lane) {
+    MGN_CUDA_TRY(cudaEventRecord(c.lane->fork[c.set], c.st));
+    MGN_CUDA_TRY(cudaStreamWaitEvent(c.lane->side, c.lane->fork[c.set], 0));
+    c.forked = true;
+    where = c.lane->side;
+  }
+  MGN_CUDA_TRY(cudaMemsetAsync(c.grads + lo, 0, sizeof(float) * (size_t)(hi - lo), where));
+  return c.hook ? c.hook->mlp_done(mi, where) : MGN_OK;
+}
+int32_t join_lane(const BwdCtx& c) {
+  if (c.lane && c.forked) {
+    MGN_CUDA_TRY(cudaEventRecord(c.lane->join, c.lane->side));
+    MGN_CUDA_TRY(cudaStreamWaitEvent(c.st, c.lane->join, 0));
+  }
+  return MGN_OK;
+}
 
 // Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
 // LayerNorm (dy = dy_a[r] + dy_b[b_idx[r]]); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
@@ -367,11 +423,11 @@ int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a,
     p.wt_img[j] = c.w->images + (size_t)im.bwd_off[l] * (kTileB / 2);
   }
   p.dz_out = c.b->dz0;
-  p.partial = c.b->partial_chain;
+  p.partial = c.pchain();
   p.pdl = c.m->knobs.pdl;
   int grid = 0;
   MGN_CUDA_TRY(mlp_backward_chain_tc(p, &grid, c.st));
-  const float* base = c.b->partial_chain;
+  const float* base = c.pchain();
   const int64_t stride = (int64_t)chain_partial_floats(p.nsteps), base_db = (int64_t)p.nsteps * 16384;
   for (int j = 0; j < p.nsteps; ++j) {
     const int l = top - j;
@@ -392,13 +448,12 @@ int32_t run_input(const BwdCtx& c, size_t mi, InputParams& p, Pieces& pc) {
   const MlpImages& im = c.m->images->mlps[mi];
   p.dz0 = (L.layer_norm || L.n_dense > 2) ? c.b->dz0 : c.b->ztop;
   p.wt_img = c.w->images + (size_t)im.bwd_off[0] * (kTileB / 2);
-  p.partial = c.b->partial_input;
+  p.partial = c.pinput();
   p.pdl = c.m->knobs.pdl;
   int grid = 0;
   MGN_CUDA_TRY(mlp_backward_input_tc(p, &grid, c.st));
-  pc.p[pc.n++] = {c.b->partial_input, (int64_t)p.nblk * 16384, grid, c.grads + L.w_off[0], (int64_t)p.nblk * 16384};
-  MGN_CUDA_TRY(reduce_pieces(pc, c.st, c.m->knobs.pdl != 0));
-  return MGN_OK;
+  pc.p[pc.n++] = {c.pinput(), (int64_t)p.nblk * 16384, grid, c.grads + L.w_off[0], (int64_t)p.nblk * 16384};
+  return finish_mlp(c, mi, pc);
 }
 
 int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const FeatRecipe& raw, const int32_t* raw_idx,
@@ -408,10 +463,9 @@ int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const Feat
   const int F = L.in[0];
   MGN_CUDA_TRY(encoder_input_bwd(c.b->dz0, raw, raw_idx, F, c.params + L.w_off[0], n_tiles,
                                  edge_rows ? c.g->E : c.g->N, edge_rows ? c.g->tile_row_start : nullptr,
-                                 c.b->partial_misc, d_raw, c.st, c.m->knobs.pdl != 0));
-  pc.p[pc.n++] = {c.b->partial_misc, (int64_t)F * 128, n_tiles, c.grads + L.w_off[0], (int64_t)F * 128};
-  MGN_CUDA_TRY(reduce_pieces(pc, c.st, c.m->knobs.pdl != 0));
-  return MGN_OK;
+                                 c.pmisc(), d_raw, c.st, c.m->knobs.pdl != 0));
+  pc.p[pc.n++] = {c.pmisc(), (int64_t)F * 128, n_tiles, c.grads + L.w_off[0], (int64_t)F * 128};
+  return finish_mlp(c, mi, pc);
 }
 
 }  // namespace
@@ -419,7 +473,6 @@ int32_t run_encoder_input(const BwdCtx& c, size_t mi, bool edge_rows, const Feat
 int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
                           const float* ef, const float* dout, float* dparams, float* dnf, void* ws,
                           size_t ws_bytes, int stage, cudaStream_t st, GradHook* hook, const FusedIo* io) {
-  auto done = [&](size_t mi) -> int32_t { return hook ? hook->mlp_done(mi) : MGN_OK; };
   if (!g->tiles_ok)
     return fail(MGN_ERR_UNSUPPORTED, "MGN_COMPUTE_BF16 needs every node to have at most 128 in-edges");
   TcWorkspace w;
@@ -432,19 +485,24 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
   const int node_tiles = (int)((N + kTile - 1) / kTile);
   const bool all = stage == kStageAll;
   BwdCtx c{m, g, params, dparams, &w, &b, st};
+  c.hook = hook;
+  // whole-pass calls reduce the weight-gradient partials of MLP i beside the kernels of MLP i-1 (stage-wise calls keep
+  // everything on the caller's stream: the halo exchanges in between are the caller's)
+  c.lane = (all && m->knobs.reduce_lane) ? reduce_lane() : nullptr;
 
   if (all || stage == MGN_STAGE_DECODE) {
     // ---- Decoder (no LayerNorm): last Dense on CUDA cores, the rest on the tensor cores
     const size_t di = m->mlps.size() - 1;
     const MlpLayout& L = m->mlps[di];
     FeatRecipe no_out{};
+    MGN_TRY(begin_mlp(c));
     MGN_CUDA_TRY(decoder_head_bwd(dout, od, params + L.w_off[nd - 1], w.saves[di].h[nd - 2], node_tiles, N, b.ztop,
-                                  b.partial_misc, io ? io->out : no_out, io ? io->val_mask : nullptr, st, m->knobs.pdl != 0));
+                                  c.pmisc(), io ? io->out : no_out, io ? io->val_mask : nullptr, st, m->knobs.pdl != 0));
     Pieces pc{};
     const int64_t hs = (int64_t)128 * od + od + 128;
-    pc.p[pc.n++] = {b.partial_misc, hs, node_tiles, dparams + L.w_off[nd - 1], (int64_t)128 * od};
-    pc.p[pc.n++] = {b.partial_misc + (int64_t)128 * od, hs, node_tiles, dparams + L.b_off[nd - 1], od};
-    pc.p[pc.n++] = {b.partial_misc + (int64_t)128 * od + od, hs, node_tiles, dparams + L.b_off[nd - 2], 128};
+    pc.p[pc.n++] = {c.pmisc(), hs, node_tiles, dparams + L.w_off[nd - 1], (int64_t)128 * od};
+    pc.p[pc.n++] = {c.pmisc() + (int64_t)128 * od, hs, node_tiles, dparams + L.b_off[nd - 1], od};
+    pc.p[pc.n++] = {c.pmisc() + (int64_t)128 * od + od, hs, node_tiles, dparams + L.b_off[nd - 2], 128};
     MGN_TRY(run_chain(c, di, false, nullptr, nullptr, nullptr, pc));
     InputParams p{};
     p.n_tiles = node_tiles;
@@ -454,7 +512,6 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     p.sink[0] = SINK_ADD_F32;
     p.f32_dst[0] = b.d_nf;
     MGN_TRY(run_input(c, di, p, pc));
-    MGN_TRY(done(di));
   }
   for (int k = mps - 1; k >= 0; --k) {
     if (!all && stage != k) continue;
@@ -462,6 +519,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
     {  // node update: nf[k+1] = nf[k] + LN(MLP_n([nf[k]; agg[k]]))
       const size_t mi = 3 + 2 * k;
       Pieces pc{};
+      MGN_TRY(begin_mlp(c));
       MGN_TRY(run_chain(c, mi, false, b.d_nf, nullptr, nullptr, pc));
       InputParams p{};
       p.n_tiles = node_tiles;
@@ -475,11 +533,11 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.sink[1] = SINK_ADD_F32;  // gradient of the aggregated messages
       p.f32_dst[1] = b.d_agg;
       MGN_TRY(run_input(c, mi, p, pc));
-      MGN_TRY(done(mi));
     }
     if (E > 0) {  // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
       const size_t mi = 2 + 2 * k;
       Pieces pc{};
+      MGN_TRY(begin_mlp(c));
       MGN_TRY(run_chain(c, mi, true, nullptr, b.d_agg, g->recv_csr, pc, d_ef_valid ? b.d_ef : nullptr));
       InputParams p{};
       p.n_tiles = g->n_edge_tiles;
@@ -504,28 +562,25 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       MGN_TRY(run_input(c, mi, p, pc));
       MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st, m->knobs.pdl != 0));
     } else {  // no edges: the edge MLP of this step has a zero gradient
-      const int64_t lo = m->mlps[2 + 2 * k].w_off[0], hi = m->mlps[3 + 2 * k].w_off[0];
-      MGN_CUDA_TRY(cudaMemsetAsync(dparams + lo, 0, sizeof(float) * (hi - lo), st));
+      MGN_TRY(zero_mlp(c, 2 + 2 * k, m->mlps[2 + 2 * k].w_off[0], m->mlps[3 + 2 * k].w_off[0]));
     }
-    MGN_TRY(done(2 + 2 * k));
   }
   if (all || stage == MGN_STAGE_ENCODE) {
     const MlpLayout& L = m->mlps[1];
     if (mps > 0 && E > 0) {
       Pieces pc{};
+      MGN_TRY(begin_mlp(c));
       MGN_TRY(run_chain(c, 1, true, nullptr, nullptr, nullptr, pc, b.d_ef));
       MGN_TRY(run_encoder_input(c, 1, true, io ? io->edge : identity_recipe(ef, m->cfg.edge_in), g->perm, nullptr, pc));
     } else {
-      const int64_t sz = m->mlps[2].w_off[0] - L.w_off[0];
-      MGN_CUDA_TRY(cudaMemsetAsync(dparams + L.w_off[0], 0, sizeof(float) * sz, st));
+      MGN_TRY(zero_mlp(c, 1, L.w_off[0], m->mlps[2].w_off[0]));
     }
-    MGN_TRY(done(1));
     Pieces pc{};
+    MGN_TRY(begin_mlp(c));
     MGN_TRY(run_chain(c, 0, false, b.d_nf, nullptr, nullptr, pc));
     MGN_TRY(run_encoder_input(c, 0, false, io ? io->node : identity_recipe(nf, m->cfg.node_in), nullptr, dnf, pc));
-    MGN_TRY(done(0));
   }
-  return MGN_OK;
+  return join_lane(c);
 }
 
 int32_t tc_backward(const mgn_model* m, const mgn_graph* g, const float* params, const float* nf,
