@@ -298,7 +298,7 @@ int32_t mgn_model_create(const mgn_model_config* cfg, mgn_model** out) {
     return fail(MGN_ERR_UNSUPPORTED,
                 "model_create: aggregate_post_residual = 1 is not built: the aggregation would have to run after the "
                 "residual add (segsum_tile call in mlp_fwd_kernel / segment_sum in pipeline.cu) and the edge MLP's "
-                "backward head would have to route d_agg[recv] into the residual path as well (run_chain dy_b)");
+                "backward head would have to route d_agg[recv] into the residual path as well (run_chain dy_b16)");
   MGN_REQUIRE(cfg->compute_mode == MGN_COMPUTE_FP32 || cfg->compute_mode == MGN_COMPUTE_BF16,
               "model_create: unknown compute_mode");
   if (cfg->compute_mode == MGN_COMPUTE_BF16)

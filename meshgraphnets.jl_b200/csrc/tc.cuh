@@ -133,10 +133,11 @@ struct ChainParams {
   int64_t M;
   const int32_t* tile_row_start;       // nullable (plain 128-row tiles)
   int head_mode;
-  // HEAD_LN: dy[r] = dy_a[r] + dy_b[b_idx ? b_idx[r] : r]   (either may be null)
-  const float* dy_a;                   // fp32 row-major ...
-  const __nv_bfloat16* dy_a_img;       // ... or bf16 tile images (gradient of the edge latent)
-  const float* dy_b;
+  // HEAD_LN: dy[r] = dy_a[r]  (fp32 row-major: node MLPs, encoders)   or
+  //          dy[r] = dy_a_img[r] + dy_b16[b_idx ? b_idx[r] : r]   (edge MLPs; either term may be null)
+  const float* dy_a;
+  const __nv_bfloat16* dy_a_img;       // bf16 tile images (gradient of the edge latent)
+  const __nv_bfloat16* dy_b16;         // bf16 row-major [nodes][128] (gradient of the aggregated messages), gathered
   const int32_t* b_idx;
   const __nv_bfloat16* xhat;           // image
   const float* rstd;                   // [rows]

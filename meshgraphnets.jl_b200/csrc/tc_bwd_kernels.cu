@@ -328,18 +328,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   } else {
     // ================================ head: LayerNorm backward (16 lanes per row, 2 x 32 rows in flight) =====
     const int lt = tid - 128, cc = lt & 15, rg = lt >> 4;  // rg in [0, 16)
-    float gs[8], gb[8], dbt[8], sc[8];
+    float gs[8], gb[8], dbt[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) gs[e] = gb[e] = dbt[e] = 0.f;
     if (p.head_mode == HEAD_LN) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) sc[e] = scale_s[cc * 8 + e];
+      const float* sc = scale_s + cc * 8;   // LayerNorm scale of this thread's 8 columns (shared memory: registers are
+                                            // the scarce resource of the head, see kDepth below)
       uint32_t t_local = 0;
       int tn = 0;
-      // gather rows of dy_b, one coalesced load per tile, fetched ONE TILE AHEAD into the other half of idx_s so that
+      // gather rows of dy_b16, one coalesced load per tile, fetched ONE TILE AHEAD into the other half of idx_s so that
       // no batch ever waits on a dependent index load (the barrier that ends a tile publishes the next tile's rows)
       auto fetch_idx = [&](int tile, uint32_t buf) {
-        if (p.dy_b && lt < kTile && tile < p.n_tiles) {
+        if (p.dy_b16 && lt < kTile && tile < p.n_tiles) {
           int64_t r0;
           int n;
           tile_rows(p.tile_row_start, p.M, tile, r0, n);
@@ -348,6 +348,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       };
       fetch_idx(blockIdx.x, 0);
       named_bar_sync(2, kHeadThreads);
+      // Batches of 32 rows (2 per thread: i = 32 b + 2 rg + u) flow through a register pipeline kDepth batches deep: the
+      // loads of batch b + kDepth - 1 are issued before batch b is computed, so that many batches' worth of bytes are in
+      // flight per thread.  In the image form everything arrives as 16-byte bf16 chunks kept as raw bits (edge MLPs: the
+      // gradient image, the gathered d_agg row, xhat: 13 registers per row), which pays for the third stage; the fp32
+      // form (node MLPs, encoders: 8 + 4 + 1 registers per row, no gather) stays double buffered.
+      constexpr int kDepth = kDyImg ? 3 : 2;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         int64_t row0;
         int cnt;
@@ -358,44 +364,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint8_t* dimg = reinterpret_cast<const uint8_t*>(p.dy_a_img) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint32_t zb = z_slot(zs) + (cc >> 3) * kTileB;
-        // Four batches of 32 rows (2 per thread: i = 32 b + 2 rg + u), double buffered: the 14 loads of batch b + 1
-        // (7 x 16 B per row) are in flight while batch b is computed, so the memory pipe never drains between batches.
-        float4 a0[kDyImg ? 1 : 4], a1[kDyImg ? 1 : 4], c0[4], c1[4];  // [buffer h][row u] at 2 h + u
-        uint4 aq[kDyImg ? 4 : 1];
-        uint4 xq[4];
-        float rs[4];
+        float4 a0[kDyImg ? 1 : 2 * kDepth], a1[kDyImg ? 1 : 2 * kDepth];  // [stage h][row u] at 2 h + u
+        uint4 aq[kDyImg ? 2 * kDepth : 1], cq[kDyImg ? 2 * kDepth : 1];
+        uint4 xq[2 * kDepth];
+        float rs[2 * kDepth];
+        uint32_t same = 0;  // bit k: row k shares its receiver with row k - 1 (its gather is the previous row's)
         auto issue = [&](int b, int h) {
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = 32 * b + rg * 2 + u, k = 2 * h + u;
-            if constexpr (kDyImg) aq[k] = make_uint4(0u, 0u, 0u, 0u);
-            else {
+            if constexpr (kDyImg) {
+              aq[k] = make_uint4(0u, 0u, 0u, 0u);
+              cq[k] = aq[k];
+            } else {
               a0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
               a1[k] = a0[k];
             }
-            c0[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-            c1[k] = c0[k];
             xq[k] = make_uint4(0u, 0u, 0u, 0u);
             rs[k] = 0.f;
             if (i < cnt) {
               const int64_t r = row0 + i;
               if constexpr (kDyImg) {  // 8 bf16 of the tile's own gradient image (same offset as the xhat chunk below)
                 if (p.dy_a_img) aq[k] = *reinterpret_cast<const uint4*>(dimg + t128_off(i, cc & 7));
+                if (p.dy_b16) {
+                  // consecutive CSR rows share their receiver: reuse the previous row's gather instead of asking L2
+                  // again (the max-carveout shared memory leaves no L1).  Only a FLAG is set here: copying the register
+                  // now would make the issue of every later load wait for the previous row's load to land.
+                  const int br = idx_c[i];
+                  if (u > 0 && br == idx_c[i - 1]) same |= 1u << k;
+                  else {
+                    same &= ~(1u << k);
+                    cq[k] = *reinterpret_cast<const uint4*>(p.dy_b16 + (int64_t)br * 128 + cc * 8);
+                  }
+                }
               } else if (p.dy_a) {
                 a0[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8);
                 a1[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
-              }
-              if (p.dy_b) {
-                // consecutive CSR rows share their receiver: reuse the previous row's gather instead of asking L2
-                // again (the max-carveout shared memory leaves no L1)
-                const int br = idx_c[i];
-                if (u > 0 && br == idx_c[i - 1]) {
-                  c0[k] = c0[k - 1];
-                  c1[k] = c1[k - 1];
-                } else {
-                  c0[k] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8);
-                  c1[k] = *reinterpret_cast<const float4*>(p.dy_b + (int64_t)br * 128 + cc * 8 + 4);
-                }
               }
               xq[k] = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
               rs[k] = p.rstd[r];
@@ -409,15 +413,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             float dy[8];
             if constexpr (kDyImg) {
               const uint32_t aw[4] = {aq[k].x, aq[k].y, aq[k].z, aq[k].w};
-              const float cv[8] = {c0[k].x, c0[k].y, c0[k].z, c0[k].w, c1[k].x, c1[k].y, c1[k].z, c1[k].w};
+              const uint4 cv = (u > 0 && ((same >> k) & 1u)) ? cq[k - 1] : cq[k];
+              const uint32_t cw[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                dy[2 * e] = __uint_as_float(aw[e] << 16) + cv[2 * e];
-                dy[2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + cv[2 * e + 1];
+                dy[2 * e] = __uint_as_float(aw[e] << 16) + __uint_as_float(cw[e] << 16);
+                dy[2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + __uint_as_float(cw[e] & 0xffff0000u);
               }
             } else {
-              dy[0] = a0[k].x + c0[k].x; dy[1] = a0[k].y + c0[k].y; dy[2] = a0[k].z + c0[k].z; dy[3] = a0[k].w + c0[k].w;
-              dy[4] = a1[k].x + c1[k].x; dy[5] = a1[k].y + c1[k].y; dy[6] = a1[k].z + c1[k].z; dy[7] = a1[k].w + c1[k].w;
+              dy[0] = a0[k].x; dy[1] = a0[k].y; dy[2] = a0[k].z; dy[3] = a0[k].w;
+              dy[4] = a1[k].x; dy[5] = a1[k].y; dy[6] = a1[k].z; dy[7] = a1[k].w;
             }
             const uint32_t xw[4] = {xq[k].x, xq[k].y, xq[k].z, xq[k].w};
             float xh[8];
@@ -453,14 +458,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             st_shared_v4(zb + t128_off(i, cc & 7), w[0], w[1], w[2], w[3]);
           }
         };
-        issue(0, 0);  // the first batch is in flight while the dZ slot of this tile is still being read
+        // the first kDepth - 1 batches are in flight while the dZ slot of this tile is still being read
+#pragma unroll
+        for (int b = 0; b < kDepth - 1; ++b) issue(b, b);
         fetch_idx(tile + gridDim.x, (t_local & 1) ^ 1);
         mbar_wait(z_empty(zs), ((t_local >> 1) & 1) ^ 1);
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L1: may write
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          if (b + 1 < 4) issue(b + 1, (b + 1) & 1);
-          compute(b, b & 1);
+          if (b + kDepth - 1 < 4) issue(b + kDepth - 1, (b + kDepth - 1) % kDepth);
+          compute(b, b % kDepth);
           if (lt == 0) trace_ev(p.trace, 0, tn);  // Lb: one batch of rows done
         }
         fence_proxy_async();
@@ -1176,6 +1183,7 @@ cudaError_t mlp_backward_chain_tc(const ChainParams& p, int* grid_out, cudaStrea
   ProfScope ps(TAG_TC_MLP_BWD, st);
   ChainParams q = p;
   q.trace = take_trace(1);
+  if (q.dy_a != nullptr && q.dy_b16 != nullptr) return cudaErrorInvalidValue;   // the gather exists in the image form only
   if (q.dy_a == nullptr && q.head_mode == HEAD_LN)   // image form (or no fp32 part at all: the last MP step's edge MLP)
     return launch_kernel(p.pdl != 0, chain::mlp_bwd_chain_kernel<true>, dim3(grid), dim3(chain::kThreads), chain::kSmemLaunch, st, q);
   return launch_kernel(p.pdl != 0, chain::mlp_bwd_chain_kernel<false>, dim3(grid), dim3(chain::kThreads), chain::kSmemLaunch, st, q);

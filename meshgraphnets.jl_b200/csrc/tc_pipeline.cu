@@ -112,7 +112,9 @@ void fill_layers(const mgn_model* m, size_t mi, const float* params, const TcWor
 
 // Scratch of the backward pass, placed after the forward workspace.
 struct BwdScratch {
-  float *d_nf = nullptr, *d_agg = nullptr;                   // fp32 gradients of the node latent / the aggregate
+  float *d_nf = nullptr, *recv_sum = nullptr;                // fp32: gradient of the node latent; receiver-adjoint sums
+  __nv_bfloat16* d_agg = nullptr;                            // gradient of the aggregated messages, bf16 [N][128]: it is the
+                                                             // staged (bf16) dX block of the node MLP, stored as it is
   __nv_bfloat16* d_ef = nullptr;                             // gradient of the edge latent: bf16 tile images (as the latent)
   __nv_bfloat16* dxs = nullptr;                              // sender adjoint rows as tile images [edge tile][2][16 KB]
   __nv_bfloat16 *dz0 = nullptr, *ztop = nullptr;             // tile images
@@ -131,7 +133,8 @@ void bwd_layout(const mgn_model* m, const mgn_graph* g, void* base, BwdScratch& 
   Bump bump(base);
   b.d_nf = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
   b.d_ef = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(edge_tiles, 1) * 2 * kTileB));
-  b.d_agg = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
+  b.recv_sum = bump.f((size_t)std::max<int64_t>(N, 1) * 128);
+  b.d_agg = bump.h((size_t)std::max<int64_t>(N, 1) * 128);
   b.dxs = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(edge_tiles, 1) * 2 * kTileB));  // tile images
   b.dz0 = static_cast<__nv_bfloat16*>(bump.raw((size_t)max_tiles * 2 * kTileB));
   b.ztop = static_cast<__nv_bfloat16*>(bump.raw((size_t)std::max<int64_t>(node_tiles, 1) * 2 * kTileB));
@@ -388,8 +391,8 @@ int32_t join_lane(const BwdCtx& c) {
 }
 
 // Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
-// LayerNorm (dy = dy_a[r] + dy_b[b_idx[r]]); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
-int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const float* dy_b,
+// LayerNorm (dy = dy_a[r], or dy_a_img[r] + dy_b16[b_idx[r]] for edge rows); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
+int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const __nv_bfloat16* dy_b16,
                   const int32_t* b_idx, Pieces& pc, const __nv_bfloat16* dy_a_img = nullptr) {
   const MlpLayout& L = c.m->mlps[mi];
   const MlpImages& im = c.m->images->mlps[mi];
@@ -404,7 +407,7 @@ int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a,
     p.head_mode = HEAD_LN;
     p.dy_a = dy_a;
     p.dy_a_img = dy_a_img;
-    p.dy_b = dy_b;
+    p.dy_b16 = dy_b16;
     p.b_idx = b_idx;
     p.xhat = sv.xhat;
     p.rstd = sv.rstd;
@@ -530,8 +533,8 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.sink[0] = SINK_ADD_F32;  // residual + direct path
       p.f32_src[0] = b.d_nf;
       p.f32_dst[0] = b.d_nf;
-      p.sink[1] = SINK_ADD_F32;  // gradient of the aggregated messages
-      p.f32_dst[1] = b.d_agg;
+      p.sink[1] = SINK_STORE_BF16;  // gradient of the aggregated messages (bf16 rows: the staged tile as it is)
+      p.bf16_dst[1] = b.d_agg;
       MGN_TRY(run_input(c, mi, p, pc));
     }
     if (E > 0) {  // edge update: ef[k+1] = ef[k] + m, agg = segsum(m)  =>  dm[j] = d_ef[j] + d_agg[recv[j]]
@@ -554,13 +557,13 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.x_is_img[2] = 1;
       p.sink[0] = SINK_STORE_IMG;   // sender adjoint rows (tile image), gathered per node through the CSC below
       p.bf16_dst[0] = b.dxs;
-      p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores into the buffer that
-      p.f32_dst[1] = b.d_agg;       // held d_agg (consumed by the chain kernel above), added to d_nf by the gather below
+      p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores, added to d_nf by the
+      p.f32_dst[1] = b.recv_sum;    // gather below
       p.sink[2] = SINK_ADD_IMG;     // edge-latent residual: d_ef = bf16(d_ef + dX), tile images, in place
       p.img_src[2] = d_ef_valid ? b.d_ef : nullptr;
       p.bf16_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p, pc));
-      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.d_agg, b.dxs, g->col_ptr, g->csc_pos, N, st, m->knobs.pdl != 0));
+      MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.recv_sum, b.dxs, g->col_ptr, g->csc_pos, N, st, m->knobs.pdl != 0));
     } else {  // no edges: the edge MLP of this step has a zero gradient
       MGN_TRY(zero_mlp(c, 2 + 2 * k, m->mlps[2 + 2 * k].w_off[0], m->mlps[3 + 2 * k].w_off[0]));
     }

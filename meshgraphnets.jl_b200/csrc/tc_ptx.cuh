@@ -189,7 +189,11 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 // One thread per role calls this; n is the role's private event counter.
 __device__ __forceinline__ void trace_ev(unsigned long long* buf, int role, int& n) {
+#ifdef MGN_ENABLE_TRACE   // debug build only (build.py --trace): the product kernels carry no trace instructions
   if (buf != nullptr && blockIdx.x == 0 && n < 512) buf[role * 512 + n++] = globaltimer_ns();
+#else
+  (void)buf; (void)role; (void)n;
+#endif
 }
 
 // ---- T128 addressing ----------------------------------------------------------------------------
