@@ -100,7 +100,9 @@ __device__ __forceinline__ void tile_rows(const FwdParams& p, int tile, int64_t&
 
 // NP = producer warps: 1 when two CTAs share an SM, 4 in the deep-ring variant (each warp stages 32 of the 128 rows, so
 // the gather instructions of a tile are issued four times faster - what bounds the latency of a single tile).
-template <int EW, int RING, int NP>
+// kResImg: the residual input is the bf16 tile image of the latent itself (edge MLPs) - all its rows are requested at
+// once as raw 16-byte chunks (same register budget as the double-buffered fp32 rows of the node MLPs).
+template <int EW, int RING, int NP, bool kResImg = false>
 __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 1) mlp_fwd_kernel(const FwdParams p) {
   using L_ = Lay<RING>;
   constexpr int kRing = RING;
@@ -363,28 +365,26 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
         // residual rows are fetched 4 per thread at a time into one half of r0/r1 while the other half is consumed
         constexpr int RG = kEpi / 16;  // row groups of the copy-out (8 or 16)
         constexpr int U = 32 / RG;     // rows per thread and 32-row batch (4 or 2)
-        float4 r0[2 * U], r1[2 * U];
+        float4 r0[kResImg ? 1 : 2 * U], r1[kResImg ? 1 : 2 * U];
+        uint4 rq[kResImg ? 4 * U : 1];   // image form: one raw 16-byte chunk per row, every row of the tile (slot U * k + u)
         const int cc = tid & 15, rg = tid >> 4;
-        const bool resid_img = p.fin_mode != FIN_LN && p.lat_img_in != nullptr;  // residual = the bf16 latent image itself
-        const bool resid = p.fin_mode != FIN_LN && p.lat_in != nullptr;
+        const bool resid = p.fin_mode != FIN_LN && (kResImg ? p.lat_img_in != nullptr : p.lat_in != nullptr);
         // false: only the aggregation is wanted (last MP step's edge latent)
         const bool write_lat = p.lat_out != nullptr || p.lat_img_out != nullptr || p.lat_bf16_out != nullptr;
         auto issue_residual = [&](int k, int h) {  // batch k covers rows 32k + rg + RG*u
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             const int i = 32 * k + rg + RG * u;
-            r0[U * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[U * h + u] = r0[U * h + u];
-            if (i < cnt) {
-              if (resid_img) {  // 8 bf16 of the tile's own image (an L2 hit: the producer staged this tile as an operand)
-                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.lat_img_in) +
+            if constexpr (kResImg) {
+              rq[U * k + u] = make_uint4(0u, 0u, 0u, 0u);
+              if (resid && i < cnt)  // an L2 hit: the producer staged this very tile as an operand a few microseconds ago
+                rq[U * k + u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.lat_img_in) +
                                                                 (size_t)tile * 2 * kTileB + (cc >> 3) * kTileB +
                                                                 t128_off(i, cc & 7));
-                r0[U * h + u] = make_float4(__uint_as_float(q.x << 16), __uint_as_float(q.x & 0xffff0000u),
-                                            __uint_as_float(q.y << 16), __uint_as_float(q.y & 0xffff0000u));
-                r1[U * h + u] = make_float4(__uint_as_float(q.z << 16), __uint_as_float(q.z & 0xffff0000u),
-                                            __uint_as_float(q.w << 16), __uint_as_float(q.w & 0xffff0000u));
-              } else if (resid) {
+            } else {
+              r0[U * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
+              r1[U * h + u] = r0[U * h + u];
+              if (resid && i < cnt) {
                 const int64_t o = (row0 + i) * 128 + cc * 8;
                 r0[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o);
                 r1[U * h + u] = *reinterpret_cast<const float4*>(p.lat_in + o + 4);
@@ -485,7 +485,12 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
         //      aggregation is shared-memory bound, so it runs BEFORE the copy-out's burst of global stores fills
         //      the SM's memory pipeline.
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C0: xhat bulk store issued
-        if (write_lat) issue_residual(0, 0);
+        if (write_lat) {
+          issue_residual(0, 0);
+          if constexpr (kResImg) issue_residual(1, 0);   // half of the tile's rows hide behind the aggregation (as many
+                                                         // registers as one fp32 batch); the other half is requested at the
+                                                         // start of the copy-out, two batches ahead of its use
+        }
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C1: first residual batch issued
         if (p.fin_mode == FIN_LN_RESID_AGG) {
           const int n0 = rp_s[130], nn = rp_s[131];
@@ -514,6 +519,10 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
         // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced), four batches of
         //      32 rows, the residual rows of batch k+1 in flight while batch k is written
         if (write_lat) {
+          if constexpr (kResImg) {
+            issue_residual(2, 0);
+            issue_residual(3, 0);
+          }
           float sc[8], bi[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -523,7 +532,7 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int h = k & 1;
-            if (k + 1 < 4) issue_residual(k + 1, h ^ 1);
+            if (!kResImg && k + 1 < 4) issue_residual(k + 1, h ^ 1);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
               const int i = 32 * k + rg + RG * u;
@@ -540,9 +549,17 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
                 m[2 * j] = fmaf(__low2float(hh), sc[2 * j], bi[2 * j]);
                 m[2 * j + 1] = fmaf(__high2float(hh), sc[2 * j + 1], bi[2 * j + 1]);
               }
-              const float4 a0 = r0[U * h + u], a1 = r1[U * h + u];
-              m[0] += a0.x; m[1] += a0.y; m[2] += a0.z; m[3] += a0.w;
-              m[4] += a1.x; m[5] += a1.y; m[6] += a1.z; m[7] += a1.w;
+              if constexpr (kResImg) {
+                const uint4 q = rq[U * k + u];
+                m[0] += __uint_as_float(q.x << 16); m[1] += __uint_as_float(q.x & 0xffff0000u);
+                m[2] += __uint_as_float(q.y << 16); m[3] += __uint_as_float(q.y & 0xffff0000u);
+                m[4] += __uint_as_float(q.z << 16); m[5] += __uint_as_float(q.z & 0xffff0000u);
+                m[6] += __uint_as_float(q.w << 16); m[7] += __uint_as_float(q.w & 0xffff0000u);
+              } else {
+                const float4 a0 = r0[U * h + u], a1 = r1[U * h + u];
+                m[0] += a0.x; m[1] += a0.y; m[2] += a0.z; m[3] += a0.w;
+                m[4] += a1.x; m[5] += a1.y; m[6] += a1.z; m[7] += a1.w;
+              }
               const int64_t o = (row0 + i) * 128 + cc * 8;
               if (p.lat_out) {
                 *reinterpret_cast<float4*>(p.lat_out + o) = make_float4(m[0], m[1], m[2], m[3]);
@@ -595,9 +612,12 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
     auto set = [&](const void* f, uint32_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     };
-    set((const void*)mlp_fwd_kernel<4, kRingShared, 1>, Lay<kRingShared>::kLaunch);
-    set((const void*)mlp_fwd_kernel<8, kRingShared, 1>, Lay<kRingShared>::kLaunch);
-    set((const void*)mlp_fwd_kernel<8, kRingDeep, 4>, Lay<kRingDeep>::kLaunch);
+    set((const void*)mlp_fwd_kernel<4, kRingShared, 1, false>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingShared, 1, false>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingDeep, 4, false>, Lay<kRingDeep>::kLaunch);
+    set((const void*)mlp_fwd_kernel<4, kRingShared, 1, true>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingShared, 1, true>, Lay<kRingShared>::kLaunch);
+    set((const void*)mlp_fwd_kernel<8, kRingDeep, 4, true>, Lay<kRingDeep>::kLaunch);
     return e;
   });
   if (ce != cudaSuccess) return ce;
@@ -608,11 +628,16 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
   q.trace = take_trace(0);
   if (grid <= n_sm) q.stagger_ns = 0u;
   const bool pdl = p.pdl != 0;
+  const bool img = p.lat_img_in != nullptr;   // residual from the bf16 latent image (edge MLPs)
+  if (img && p.lat_in != nullptr) return cudaErrorInvalidValue;
   if (p.epi_warps == 4)
-    return launch_kernel(pdl, mlp_fwd_kernel<4, kRingShared, 1>, dim3(grid), dim3(32 * 6), Lay<kRingShared>::kLaunch, st, q);
+    return img ? launch_kernel(pdl, mlp_fwd_kernel<4, kRingShared, 1, true>, dim3(grid), dim3(32 * 6), Lay<kRingShared>::kLaunch, st, q)
+               : launch_kernel(pdl, mlp_fwd_kernel<4, kRingShared, 1, false>, dim3(grid), dim3(32 * 6), Lay<kRingShared>::kLaunch, st, q);
   if (p.deep_ring && p.n_tiles <= n_sm)
-    return launch_kernel(pdl, mlp_fwd_kernel<8, kRingDeep, 4>, dim3(grid), dim3(32 * 13), Lay<kRingDeep>::kLaunch, st, q);
-  return launch_kernel(pdl, mlp_fwd_kernel<8, kRingShared, 1>, dim3(grid), dim3(32 * 10), Lay<kRingShared>::kLaunch, st, q);
+    return img ? launch_kernel(pdl, mlp_fwd_kernel<8, kRingDeep, 4, true>, dim3(grid), dim3(32 * 13), Lay<kRingDeep>::kLaunch, st, q)
+               : launch_kernel(pdl, mlp_fwd_kernel<8, kRingDeep, 4, false>, dim3(grid), dim3(32 * 13), Lay<kRingDeep>::kLaunch, st, q);
+  return img ? launch_kernel(pdl, mlp_fwd_kernel<8, kRingShared, 1, true>, dim3(grid), dim3(32 * 10), Lay<kRingShared>::kLaunch, st, q)
+             : launch_kernel(pdl, mlp_fwd_kernel<8, kRingShared, 1, false>, dim3(grid), dim3(32 * 10), Lay<kRingShared>::kLaunch, st, q);
 }
 
 }  // namespace tc
