@@ -1,5 +1,10 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -s 540 -c 334 --csv --log-file gpurun_out/r2_launches_bf16.csv python bench.py --steps 2 --warmup 1 --no-graph --no-shooting-leg > gpurun_out/r2_ncu_launches.log 2>&1
-ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"mlp_fwd_kernel|mlp_bwd_chain_kernel|mlp_bwd_input_kernel" -s 291 -c 97 --csv --log-file gpurun_out/r2_dram_bytes.csv python bench.py --steps 2 --warmup 1 --no-graph --no-shooting-leg > gpurun_out/r2_ncu_dram.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mlp_fwd_kernel -s 104 -c 2 -o gpurun_out/r2_prof_fwd -f python bench.py --steps 1 --warmup 1 --no-graph --no-shooting-leg > gpurun_out/r2_ncu_fwd.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"mlp_bwd_chain_kernel|mlp_bwd_input_kernel" -s 70 -c 4 -o gpurun_out/r2_prof_bwd -f python bench.py --steps 1 --warmup 1 --no-graph --no-shooting-leg > gpurun_out/r2_ncu_bwd.log 2>&1
-ls -la gpurun_out/r2_launches_bf16.csv gpurun_out/r2_dram_bytes.csv gpurun_out/*.ncu-rep
+( time python -c "import __graft_entry__ as g; g.smoke()" ) 2>&1 | tail -8
+( time python bench.py > gpurun_out/r2_bench_default.json 2> gpurun_out/r2_bench_default.err ) 2>&1 | tail -4
+python - <<PY
+import json
+d=json.load(open("gpurun_out/r2_bench_default.json"))
+print(d["ms_per_step"], d["value"], d["e2e"], d["batch1"]["ms_per_step"])
+print(json.dumps(d.get("multiple_shooting_sharded"))[:400])
+print({k:v for k,v in d["roofline"].items() if k!="note"})
+PY
+( time python bench.py --impl reference --steps 5 --warmup 2 ) 2>&1 | tail -5 | cut -c1-600
