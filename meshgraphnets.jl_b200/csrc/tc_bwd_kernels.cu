@@ -643,20 +643,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           ++xc;
           continue;
         }
-        int64_t srow[RPW];
+        int32_t srow[RPW];
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {  // the index loads of this lane are in flight together
           const int r = lane + 32 * (pw * RPW + rr);
-          srow[rr] = r < cnt ? (idx ? (int64_t)idx[row0 + r] : row0 + r) : 0;
+          srow[rr] = r < cnt ? (idx ? idx[row0 + r] : (int32_t)(row0 + r)) : 0;
         }
+        // One cp.async instruction covers TWO source rows with sixteen lanes each (a 256-byte row = two lines): four lines
+        // per instruction instead of the 32 of a lane-per-row mapping (the load/store unit processes one line per cycle
+        // and is shared with the epilogue's shared-memory traffic).  The row index is fetched from its lane by a shuffle.
+        const int sub = lane >> 4, ch = lane & 15;
+        const uint32_t dst_c = dst + (uint32_t)(ch >> 3) * (uint32_t)kTileB;
+        const uint8_t* src_c = reinterpret_cast<const uint8_t*>(src_base) + ch * 16;
 #pragma unroll
         for (int rr = 0; rr < RPW; ++rr) {
-          const int r = lane + 32 * (pw * RPW + rr);
-          const bool ok = r < cnt;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + srow[rr] * 128);
+          const int g32 = 32 * (pw * RPW + rr);
 #pragma unroll
-          for (int c = 0; c < 16; ++c)
-            cp_async16(dst + (c >> 3) * kTileB + t128_off(r, c & 7), src + c * 16, ok ? 16u : 0u);
+          for (int i = 0; i < 16; ++i) {
+            const int rl = 2 * i + sub;
+            const int r = g32 + rl;
+            const int64_t src_row = __shfl_sync(0xffffffffu, srow[rr], rl);
+            cp_async16(dst_c + t128_off(r, ch & 7), src_c + src_row * 256, r < cnt ? 16u : 0u);
+          }
         }
         cp_async_arrive_noinc(x_full(xs));
         if (lead) trace_ev(p.trace, 3, tn);  // P2: gather issued

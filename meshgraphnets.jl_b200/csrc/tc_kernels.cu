@@ -178,15 +178,15 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
       tile_rows(p, tile, row0, cnt);
       // source rows of this lane's 4 tile rows, for both gather index vectors: all index loads of the tile
       // are issued together, so no K-block waits on a dependent index load
-      int64_t src0[RPW], src1[RPW];
+      int32_t src0[RPW], src1[RPW];
 #pragma unroll
       for (int rr = 0; rr < RPW; ++rr) {
         const int r = lane + 32 * (pw * RPW + rr);
         const bool ok = r < cnt;
         const int32_t* i0 = p.in_mode == IN_RAW ? p.raw_idx : (p.in_mode == IN_GATHER3 ? p.idx0 : nullptr);
         const int32_t* i1 = p.in_mode == IN_GATHER3 ? p.idx1 : nullptr;
-        src0[rr] = ok ? (i0 ? (int64_t)i0[row0 + r] : row0 + r) : 0;
-        src1[rr] = ok ? (i1 ? (int64_t)i1[row0 + r] : row0 + r) : 0;
+        src0[rr] = ok ? (i0 ? i0[row0 + r] : (int32_t)(row0 + r)) : 0;
+        src1[rr] = ok ? (i1 ? i1[row0 + r] : (int32_t)(row0 + r)) : 0;
       }
       for (int l = 0; l < L; ++l) {
         for (int kb = 0; kb < p.nkb[l]; ++kb) {
@@ -236,14 +236,24 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
               } else {
                 src_base = seg == 0 ? p.x0 : p.x1;
               }
+              // One cp.async instruction covers FOUR source rows with eight lanes each: eight lanes read the 128
+              // contiguous bytes (one line) of a row's K-block half, so an instruction touches 4 lines instead of the 32 of
+              // a lane-per-row mapping - the load/store unit processes one line per cycle, and it is shared with everything
+              // the epilogue warps (of both resident CTAs) do.  The row index lives in the lane that loaded it (lane == row
+              // of the 32-row group) and is fetched with a shuffle.
+              const int sub = lane >> 3, ch = lane & 7;
+              const uint8_t* src_kb = reinterpret_cast<const uint8_t*>(src_base + (kb & 1) * 64) + ch * 16;
 #pragma unroll
               for (int rr = 0; rr < RPW; ++rr) {
-                const int r = lane + 32 * (pw * RPW + rr);
-                const bool ok = r < cnt;
-                const int64_t src_row = ok ? (which == 0 ? src0[rr] : (which == 1 ? src1[rr] : row0 + r)) : 0;
-                const uint8_t* src = reinterpret_cast<const uint8_t*>(src_base + src_row * 128 + (kb & 1) * 64);
+                const int g32 = 32 * (pw * RPW + rr);
+                const int32_t mine = which == 0 ? src0[rr] : (which == 1 ? src1[rr] : (int32_t)min(row0 + g32 + lane, p.M - 1));
 #pragma unroll
-                for (int c = 0; c < 8; ++c) cp_async16(dst + t128_off(r, c), src + c * 16, ok ? 16u : 0u);
+                for (int i = 0; i < 8; ++i) {
+                  const int rl = 4 * i + sub;
+                  const int r = g32 + rl;
+                  const int64_t src_row = __shfl_sync(0xffffffffu, mine, rl);
+                  cp_async16(dst + t128_off(r, ch), src_kb + src_row * 256, r < cnt ? 16u : 0u);
+                }
               }
               cp_async_arrive_noinc(full_bar(s));
             }
