@@ -356,11 +356,14 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
         }
         // the shared activation tile is about to be overwritten: every thread must be done reading the
         // previous tile's copy-out / aggregation, and a pending bulk store must have read it
-        if (tid == 0 && store_pending) {
-          bulk_wait_read0();
-          store_pending = false;
+        // (layers > 0 of an inference pass: the tile's last reader was this layer's MMA, which has completed - no barrier)
+        if (l == 0 || p.save_h[0] != nullptr) {
+          if (tid == 0 && store_pending) {
+            bulk_wait_read0();
+            store_pending = false;
+          }
+          named_bar_sync(1, kEpi);
         }
-        named_bar_sync(1, kEpi);
         if (l == 0 && p.fin_mode == FIN_LN_RESID_AGG) {
           // tile-local CSR row pointer -> shared memory (read by the aggregation after two more barriers)
           const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
@@ -403,18 +406,93 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
           }
         };
         float mean = 0.f, rstd = 1.f;
-        if (last) {  // LayerNorm statistics in ONE extra pass over TMEM: sums of the data shifted by the row's first
-                     // element (the shifted-data formula keeps the fp32 variance accurate), biased variance
-          // sums over the left and the right 64 columns separately, then added: the same arithmetic for both thread
-          // layouts (mirrored by oracle/mgn_oracle_bf16.py)
+        bool arrived = false;   // epi_done already signalled (the accumulator was drained into registers)
+        if constexpr (kHalves == 2) {
+          // Two threads per row: the 64 accumulator columns of this thread are loaded with TWO tcgen05.ld in flight and ONE
+          // wait, and stay in registers - the LayerNorm layer reads TMEM once (statistics and normalisation from the same
+          // registers) and releases the accumulator to the MMA warp before the statistics are even exchanged.
+          const uint32_t bs = s_base + kSmemBias + (uint32_t)(l * 128 + c_lo * 32) * 4u;   // this thread's 64 biases
+          auto store_chunk = [&](int c, const uint32_t (&w)[16]) {
+            const uint32_t tb = s_h + (c >> 1) * kTileB;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              st_shared_v4(tb + t128_off(row, (c & 1) * 4 + q4), w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
+          };
+          if (!last) {
+#pragma unroll 1
+            for (int cc2 = 0; cc2 < 2; ++cc2) {
+              uint32_t r[32], w[16];
+              tmem_ld32_issue(t_lane + (c_lo + cc2) * 32, r);
+              tmem_ld_wait();
+              tmem_regs_fence(r);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 b4 = ld_shared_f4(bs + (uint32_t)(cc2 * 128 + q * 16));
+                w[2 * q] = pack_bf16x2_relu(__uint_as_float(r[4 * q]) + b4.x, __uint_as_float(r[4 * q + 1]) + b4.y);
+                w[2 * q + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * q + 2]) + b4.z, __uint_as_float(r[4 * q + 3]) + b4.w);
+              }
+              store_chunk(c_lo + cc2, w);
+            }
+          } else {
+            // LayerNorm statistics: sums of the data shifted by the row's first element (the shifted-data formula keeps the
+            // fp32 variance accurate), biased variance; sums over the left and the right 64 columns separately, in column
+            // order, then added: the same arithmetic for both thread layouts (mirrored by oracle/mgn_oracle_bf16.py)
+            // (the 64 columns do not fit in registers beside the loop state at 96 registers per thread: TMEM is read twice)
+            uint32_t r[32], r_first;
+            float shift = 0.f, s = 0.f, q = 0.f;
+#pragma unroll 1
+            for (int cc2 = 0; cc2 < 2; ++cc2) {
+              if (cc2 == 0) tmem_ld1_issue(t_lane, r_first);
+              tmem_ld32_issue(t_lane + (c_lo + cc2) * 32, r);
+              tmem_ld_wait();
+              tmem_regs_fence(r);
+              if (cc2 == 0) shift = __uint_as_float(r_first) + bias_s[l * 128];
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = ld_shared_f4(bs + (uint32_t)(cc2 * 128 + g * 16));
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float d = __uint_as_float(r[4 * g + e]) + bb[e] - shift;
+                  s += d;
+                  q = fmaf(d, d, q);
+                }
+              }
+            }
+            stat_s[half * 128 + row] = make_float2(s, q);
+            named_bar_sync(1, kEpi);
+            const float2 a = stat_s[row], b = stat_s[128 + row];
+            s = a.x + b.x;
+            q = a.y + b.y;
+            const float ms = s * (1.f / 128.f);
+            mean = shift + ms;
+            q = fmaxf(q * (1.f / 128.f) - ms * ms, 0.f) * 128.f;
+            rstd = 1.f / sqrtf(q * (1.f / 128.f) + p.eps);
+            if (p.save_rstd && row < cnt && half == 0) p.save_rstd[row0 + row] = rstd;
+#pragma unroll 1
+            for (int cc2 = 0; cc2 < 2; ++cc2) {
+              uint32_t w[16];
+              tmem_ld32_issue(t_lane + (c_lo + cc2) * 32, r);
+              tmem_ld_wait();
+              tmem_regs_fence(r);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = ld_shared_f4(bs + (uint32_t)(cc2 * 128 + g * 16));
+                w[2 * g] = pack_bf16x2((__uint_as_float(r[4 * g]) + b4.x - mean) * rstd, (__uint_as_float(r[4 * g + 1]) + b4.y - mean) * rstd);
+                w[2 * g + 1] = pack_bf16x2((__uint_as_float(r[4 * g + 2]) + b4.z - mean) * rstd, (__uint_as_float(r[4 * g + 3]) + b4.w - mean) * rstd);
+              }
+              store_chunk(c_lo + cc2, w);
+            }
+          }
+        } else {
+        if (last) {  // LayerNorm statistics in ONE extra pass over TMEM (one thread per row: 128 columns do not fit in registers)
           float s = 0.f, q = 0.f, s_lo = 0.f, q_lo = 0.f, shift = 0.f;
-          if (kHalves == 2) shift = tmem_ld1(t_lane) + bias_s[l * 128];  // both halves shift by the row's first element
 #pragma unroll 1
           for (int c = c_lo; c < c_hi; ++c) {
             float v[32];
             tmem_ld32(t_lane + c * 32, v);
-            if (kHalves == 1 && c == 0) shift = v[0] + bias_s[l * 128];
-            if (kHalves == 1 && c == 2) {
+            if (c == 0) shift = v[0] + bias_s[l * 128];
+            if (c == 2) {
               s_lo = s;
               q_lo = q;
               s = 0.f;
@@ -427,16 +505,8 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
               q = fmaf(d, d, q);
             }
           }
-          if (kHalves == 2) {
-            stat_s[half * 128 + row] = make_float2(s, q);
-            named_bar_sync(1, kEpi);
-            const float2 a = stat_s[row], b = stat_s[128 + row];
-            s = a.x + b.x;
-            q = a.y + b.y;
-          } else {
-            s = s_lo + s;
-            q = q_lo + q;
-          }
+          s = s_lo + s;
+          q = q_lo + q;
           const float ms = s * (1.f / 128.f);
           mean = shift + ms;
           q = fmaxf(q * (1.f / 128.f) - ms * ms, 0.f) * 128.f;
@@ -466,6 +536,7 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
           for (int q4 = 0; q4 < 4; ++q4)
             st_shared_v4(tb + t128_off(row, (c & 1) * 4 + q4), w[4 * q4], w[4 * q4 + 1], w[4 * q4 + 2], w[4 * q4 + 3]);
         }
+        }
         fence_proxy_async();
         tc_fence_before();
         __nv_bfloat16* save = last ? p.save_xhat : p.save_h[l];
@@ -482,7 +553,7 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
           continue;
         }
         // ---- last layer: TMEM is drained -> the MMA warp may start the next tile
-        mbar_arrive(epi_done);
+        if (!arrived) mbar_arrive(epi_done);
         named_bar_sync(1, kEpi);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: LayerNorm done, xhat staged
         if (save && tid == 0) {
@@ -533,12 +604,10 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
             issue_residual(2, 0);
             issue_residual(3, 0);
           }
-          float sc[8], bi[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            sc[j] = ln_s[cc * 8 + j];
-            bi[j] = ln_s[128 + cc * 8 + j];
-          }
+          const uint32_t ln_a = s_base + kSmemLn + (uint32_t)cc * 32u;
+          const float4 s0 = ld_shared_f4(ln_a), s1 = ld_shared_f4(ln_a + 16u), b0 = ld_shared_f4(ln_a + 512u), b1 = ld_shared_f4(ln_a + 528u);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int h = k & 1;
