@@ -40,9 +40,15 @@ __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __
 // Chain kernel
 // ======================================================================================================
 namespace chain {
-constexpr int kThreads = 448;  // warps 0-3 epilogue, 4-11 head (LayerNorm backward), 12 producer, 13 MMA
+// Warps 0-7 epilogue (two threads per tile row: thread (row, half) owns 64 accumulator columns), 8-15 head (LayerNorm
+// backward), 16 producer, 17 MMA issue, 18-19 idle (they complete the fifth warpgroup).  The launch allocates 96 registers
+// per thread; setmaxnreg then moves them where they are needed: the head's three-deep load pipeline gets 128, the
+// epilogue keeps 88, the producer / MMA warpgroup 40.
+constexpr int kThreads = 640;
+constexpr int kEpiThreads = 256;
 constexpr int kHeadThreads = 256;
-constexpr int kWarpP = 12, kWarpM = 13;
+constexpr int kWarpH = 8, kWarpP = 16, kWarpM = 17;
+constexpr int kRegsHead = 128, kRegsEpi = 88, kRegsMisc = 40;   // 256 * 128 + 256 * 88 + 128 * 40 <= 640 * 96
 // dZ slots: 0-1 hold the head's output (top dZ of a tile; the head may run a whole tile ahead of the MMAs),
 // 2-3 the epilogue's outputs (dZ of the layers below, alternating).  H and W^T images stream through 2-slot rings.
 constexpr int kZ = 4, kH = 2, kW = 2;
@@ -51,11 +57,16 @@ constexpr uint32_t kSmemH = kSmemZ + kZ * kImg;
 constexpr uint32_t kSmemW = kSmemH + kH * kImg;
 constexpr uint32_t kSmemScale = kSmemW + kW * kTileB;         // ln scale [128]
 constexpr uint32_t kSmemIdx = kSmemScale + 512;               // gather rows of dy_b of this and of the next tile, 2 x 128 ints
-constexpr uint32_t kSmemBar = kSmemIdx + 1024;                // (the head's final [8][3][128] reduction reuses a dZ slot)
+constexpr uint32_t kSmemRstd = kSmemIdx + 1024;               // rstd of the rows of this and of the next tile, 2 x 128 floats
+constexpr uint32_t kSmemTrs = kSmemRstd + 1024;                // head: (first row, row count) of its next 16 tiles, int2 ring
+constexpr uint32_t kSmemBar = kSmemTrs + 128;                 // (the head's final [8][3][128] reduction reuses a dZ slot)
 constexpr uint32_t kNumBar = 2 * kZ + 2 * kH + 2 * kW + 4;
 constexpr uint32_t kSmemTmem = kSmemBar + 8 * kNumBar;
 constexpr uint32_t kSmemTotal = kSmemTmem + 16;
-constexpr uint32_t kSmemLaunch = kSmemTotal + 1024;
+// Everything the SM has (227 KB): the dynamic region starts 1024-byte aligned in practice (no static shared memory), so the
+// alignment slack is the 336 bytes that are left; the kernel traps if the aligned layout does not fit.
+constexpr uint32_t kSmemLaunch = 232448;
+static_assert(kSmemTotal <= kSmemLaunch, "chain kernel shared memory");
 
 // kDyImg: the fp32 part of dy comes as bf16 tile images (edge MLPs) - kept as raw bits until it is consumed, which frees
 // 16 registers of the head's double-buffered loads compared with the fp32 row-major form (node MLPs, encoders).
@@ -64,8 +75,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
+  if (s_base + kSmemTotal > smem_u32(smem_raw) + kSmemLaunch) __trap();
   float* scale_s = reinterpret_cast<float*>(smem + kSmemScale);
   int* idx_s = reinterpret_cast<int*>(smem + kSmemIdx);
+  float* rstd_s = reinterpret_cast<float*>(smem + kSmemRstd);
   const uint32_t bar0 = s_base + kSmemBar;
   auto z_full = [&](int s) { return bar0 + 8u * s; };
   auto z_empty = [&](int s) { return bar0 + 8u * (kZ + s); };
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       mbar_init(w_empty(s), 1);
     }
     mbar_init(acc_full, 1);
-    mbar_init(acc_empty, 128);
+    mbar_init(acc_empty, kEpiThreads);
     mbar_init(done_bar, 1);
     fence_mbar_init();
   }
@@ -112,12 +125,35 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == kWarpP) {
+  if (warp >= kWarpP) {
+   reg_dealloc<kRegsMisc>();                              // the whole warpgroup 16-19
+   if (warp == kWarpP) {
     // ================================ producer (one thread: bulk copies only) ========================
     if (lane == 0) {
       uint32_t hc = 0, wc = 0, t_local = 0;
       int tn = 0;
+      // Everything a tile streams from HBM is asked into L2 one tile ahead: the head's register pipeline and the two-slot
+      // H ring then wait for an L2 hit instead of a DRAM access under load (measured: ~3 us).
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= p.n_tiles) return;
+        for (int j = 0; j < ns; ++j)
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.h_img[j]) + (size_t)tile * kImg, kImg);
+        if (p.head_mode == HEAD_IMAGE) {
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.z_top) + (size_t)tile * kImg, kImg);
+          return;
+        }
+        bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg, kImg);
+        if (p.dy_a_img) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.dy_a_img) + (size_t)tile * kImg, kImg);
+        if (p.dy_a) {
+          int64_t r0;
+          int n;
+          tile_rows(p.tile_row_start, p.M, tile, r0, n);
+          if (n > 0) bulk_prefetch_l2(p.dy_a + r0 * 128, (uint32_t)n * 512u);
+        }
+      };
+      prefetch_tile(blockIdx.x);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
+        prefetch_tile(tile + gridDim.x);
         if (p.head_mode == HEAD_IMAGE) {
           const uint32_t s = t_local & 1;
           mbar_wait(z_empty(s), ((t_local >> 1) & 1) ^ 1);
@@ -142,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         }
       }
     }
-  } else if (warp == kWarpM) {
+   } else if (warp == kWarpM) {
     // ================================ MMA issue ================================
     if (lane == 0) {
       const uint32_t idesc_k = umma_idesc(128, 128, false, false);
@@ -172,8 +208,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             const uint32_t ws = wc % kW;
             mbar_wait(w_full(ws), (wc / kW) & 1);
             tc_fence_after();
-            for (int k = 0; k < 4; ++k)
-              umma(tmem, desc_kmajor(z_slot(zs) + kb * kTileB, k), desc_kmajor(w_slot(ws), k), idesc_k, (kb | k) != 0);
+            const uint32_t a_lo = kdesc_lo(z_slot(zs) + kb * kTileB), b_lo = kdesc_lo(w_slot(ws));
+            umma_lo(tmem, a_lo, b_lo, idesc_k, kb != 0);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) umma_lo(tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_k, true);
             umma_commit(w_empty(ws));
           }
           umma_commit(acc_full);
@@ -184,9 +222,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           trace_ev(p.trace, 1, tn);  // M4: H ready
           tc_fence_after();
           const uint32_t d_w = tmem + 128u * (1 + j);
-          for (int ks = 0; ks < 8; ++ks)
-            umma(d_w, desc_mnmajor(h_slot(hs), (uint32_t)kTileB, ks), desc_mnmajor(z_slot(zs), (uint32_t)kTileB, ks),
-                 idesc_mn, (t_local | ks) != 0);
+          {
+            const uint32_t a_lo = mndesc_lo(h_slot(hs), (uint32_t)kTileB), b_lo = mndesc_lo(z_slot(zs), (uint32_t)kTileB);
+            umma_lo(d_w, a_lo, b_lo, idesc_mn, t_local != 0);
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks) umma_lo(d_w, a_lo + 128 * ks, b_lo + 128 * ks, idesc_mn, true);
+          }
           umma_commit(h_empty(hs));
           umma_commit(z_empty(zs));
           ++hc;
@@ -194,13 +235,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       }
       umma_commit(done_bar);
     }
-  } else if (warp < 4) {
-    // ================================ epilogue (thread == row) ================================
-    const int row = tid;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+   }   // warps 18-19: idle
+  } else if (warp < kWarpH) {
+    // ================================ epilogue (thread == (row, column half)) ================================
+    reg_dealloc<kRegsEpi>();                              // warpgroups 0-3, 4-7
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t hc = 0, t_local = 0, acc_par = 0;
     int tn = 0;
-    // bias-gradient partials: this thread sums 8 columns (one 16-byte chunk) over one eighth of the rows, per step
+    // bias-gradient partials: this thread sums 8 columns (one 16-byte chunk) over one sixteenth of the rows, per step
     float db0[8], db1[8], db2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) db0[e] = db1[e] = db2[e] = 0.f;
@@ -220,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E2: H there, Z slot free
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 2 * half; c < 2 * half + 2; ++c) {
           float v[32];
           tmem_ld32(t_lane + c * 32, v);
           const uint32_t hb = h_slot(hs) + (c >> 1) * kTileB, zb = z_slot(zs) + (c >> 1) * kTileB;
@@ -242,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         fence_proxy_async();
         tc_fence_before();
         mbar_arrive(acc_empty);
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: masked dZ written
         const bool last = j == ns - 1;
         if (tid == 0) {
@@ -262,8 +305,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
 #pragma unroll
           for (int e = 0; e < 8; ++e) t8[e] = 0.f;
 #pragma unroll 4
-          for (uint32_t rr = 0; rr < 16; ++rr) {
-            const uint32_t jr = grp * 16u + rr;
+          for (uint32_t rr = 0; rr < 8; ++rr) {
+            const uint32_t jr = grp * 8u + rr;
             const uint4 q = ld_shared_v4(zb2 + jr * 128u + ((chunk ^ (jr & 7u)) << 4));
             const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -279,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
             else db2[e] += t8[e];
           }
         }
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E4: column sums done
         if (tid == 0) {
           if (last) {
@@ -296,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     tc_fence_after();
     for (int j = 0; j < ns; ++j) {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * half; c < 2 * half + 2; ++c) {
         float v[32];
         tmem_ld32(t_lane + 128u * (1 + j) + c * 32, v);
         float4* dst = reinterpret_cast<float4*>(my_partial + (size_t)j * 16384 + (size_t)row * 128 + c * 32);
@@ -304,9 +347,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
-    // bias gradients: [8 row groups][3 steps][128] through an epilogue dZ slot (all MMAs and the last dZ bulk
+    // bias gradients: [16 row groups][3 steps][128] through an epilogue dZ slot (all MMAs and the last dZ bulk
     // store are done), then a fixed-order sum over the row groups
-    named_bar_sync(1, 128);
+    named_bar_sync(1, kEpiThreads);
     {
       float* red = reinterpret_cast<float*>(smem + kSmemZ + 2 * kImg);
       const int col0 = (int)((((uint32_t)tid >> 3) & 1u) * 64u + ((uint32_t)tid & 7u) * 8u), grp = tid >> 4;
@@ -316,18 +359,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         red[(grp * 3 + 1) * 128 + col0 + e] = db1[e];
         red[(grp * 3 + 2) * 128 + col0 + e] = db2[e];
       }
-      named_bar_sync(1, 128);
-      for (int j = 0; j < ns; ++j) {
-        float t = 0.f;
+      named_bar_sync(1, kEpiThreads);
+      if (tid < 128)
+        for (int j = 0; j < ns; ++j) {
+          float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) t += red[(g * 3 + j) * 128 + tid];
-        my_partial[(size_t)ns * 16384 + (size_t)(j + 1) * 128 + tid] = t;
-      }
+          for (int g = 0; g < 16; ++g) t += red[(g * 3 + j) * 128 + tid];
+          my_partial[(size_t)ns * 16384 + (size_t)(j + 1) * 128 + tid] = t;
+        }
     }
     if (tid == 0) bulk_wait0();
   } else {
     // ================================ head: LayerNorm backward (16 lanes per row, 2 x 32 rows in flight) =====
-    const int lt = tid - 128, cc = lt & 15, rg = lt >> 4;  // rg in [0, 16)
+    reg_alloc<kRegsHead>();                               // warpgroups 8-11, 12-15
+    const int lt = tid - 32 * kWarpH, cc = lt & 15, rg = lt >> 4;  // rg in [0, 16)
     float gs[8], gb[8], dbt[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) gs[e] = gb[e] = dbt[e] = 0.f;
@@ -338,15 +383,44 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       int tn = 0;
       // gather rows of dy_b16, one coalesced load per tile, fetched ONE TILE AHEAD into the other half of idx_s so that
       // no batch ever waits on a dependent index load (the barrier that ends a tile publishes the next tile's rows)
-      auto fetch_idx = [&](int tile, uint32_t buf) {
+      // (the load is issued at the top of a tile and its value stored at the bottom: a store right behind the load would
+      // stall the thread for a whole memory latency in front of the tile's first batch)
+      auto load_idx = [&](int tile) -> int {   // kernel start only: reads tile_row_start itself
+        int v = 0;
         if (p.dy_b16 && lt < kTile && tile < p.n_tiles) {
           int64_t r0;
           int n;
           tile_rows(p.tile_row_start, p.M, tile, r0, n);
-          idx_s[buf * kTile + lt] = lt < n ? (p.b_idx ? p.b_idx[r0 + lt] : (int)(r0 + lt)) : 0;
+          if (lt < n) v = p.b_idx ? p.b_idx[r0 + lt] : (int)(r0 + lt);
         }
+        return v;
       };
-      fetch_idx(blockIdx.x, 0);
+      // rstd of a tile's rows travels the same way (one load per row and tile instead of one per row and 16-lane group)
+      auto load_rstd = [&](int tile) -> float {
+        float v = 0.f;
+        if (lt < kTile && tile < p.n_tiles) {
+          int64_t r0;
+          int n;
+          tile_rows(p.tile_row_start, p.M, tile, r0, n);
+          if (lt < n) v = p.rstd[r0 + lt];
+        }
+        return v;
+      };
+      if (lt < kTile) {
+        idx_s[lt] = load_idx(blockIdx.x);
+        rstd_s[lt] = load_rstd(blockIdx.x);
+      }
+      // Row ranges of the CTA's tiles come from a 16-entry ring in shared memory that one thread refills 15 tiles ahead:
+      // tile_row_start is a dependent global load (~2 us under load) that used to stand in front of every tile TWICE - at
+      // its top, and again in front of the index / rstd loads of the next tile.
+      int2* trs_s = reinterpret_cast<int2*>(smem + kSmemTrs);
+      auto tile_range = [&](int tile) -> int2 {
+        int64_t r0;
+        int n;
+        tile_rows(p.tile_row_start, p.M, tile, r0, n);
+        return make_int2((int)r0, n);
+      };
+      if (lt < 16 && blockIdx.x + lt * (int)gridDim.x < p.n_tiles) trs_s[lt] = tile_range(blockIdx.x + lt * gridDim.x);
       named_bar_sync(2, kHeadThreads);
       // Batches of 32 rows (2 per thread: i = 32 b + 2 rg + u) flow through a register pipeline kDepth batches deep: the
       // loads of batch b + kDepth - 1 are issued before batch b is computed, so that many batches' worth of bytes are in
@@ -355,11 +429,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       // form (node MLPs, encoders: 8 + 4 + 1 registers per row, no gather) stays double buffered.
       constexpr int kDepth = kDyImg ? 3 : 2;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
-        int64_t row0;
-        int cnt;
-        tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
+        const int2 rc = trs_s[t_local & 15];
+        const int64_t row0 = rc.x;
+        const int cnt = rc.y;
         const uint32_t zs = t_local & 1;
         const int* idx_c = idx_s + (t_local & 1) * kTile;
+        const float* rstd_c = rstd_s + (t_local & 1) * kTile;
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L0: tile start
         const uint8_t* ximg = reinterpret_cast<const uint8_t*>(p.xhat) + (size_t)tile * kImg + (cc >> 3) * kTileB;
         const uint8_t* dimg = reinterpret_cast<const uint8_t*>(p.dy_a_img) + (size_t)tile * kImg + (cc >> 3) * kTileB;
@@ -367,7 +442,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         float4 a0[kDyImg ? 1 : 2 * kDepth], a1[kDyImg ? 1 : 2 * kDepth];  // [stage h][row u] at 2 h + u
         uint4 aq[kDyImg ? 2 * kDepth : 1], cq[kDyImg ? 2 * kDepth : 1];
         uint4 xq[2 * kDepth];
-        float rs[2 * kDepth];
         uint32_t same = 0;  // bit k: row k shares its receiver with row k - 1 (its gather is the previous row's)
         auto issue = [&](int b, int h) {
 #pragma unroll
@@ -381,7 +455,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
               a1[k] = a0[k];
             }
             xq[k] = make_uint4(0u, 0u, 0u, 0u);
-            rs[k] = 0.f;
             if (i < cnt) {
               const int64_t r = row0 + i;
               if constexpr (kDyImg) {  // 8 bf16 of the tile's own gradient image (same offset as the xhat chunk below)
@@ -402,7 +475,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
                 a1[k] = *reinterpret_cast<const float4*>(p.dy_a + r * 128 + cc * 8 + 4);
               }
               xq[k] = *reinterpret_cast<const uint4*>(ximg + t128_off(i, cc & 7));
-              rs[k] = p.rstd[r];
             }
           }
         };
@@ -446,11 +518,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
               s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
             const float m1 = s1 * (1.f / 128.f), m2 = s2 * (1.f / 128.f);
+            const float rs = rstd_c[i];   // rows >= cnt: 0 (and every other factor is 0 too)
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float a = rs[k] * (dxh[2 * e] - m1 - xh[2 * e] * m2);
-              const float b2 = rs[k] * (dxh[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
+              const float a = rs * (dxh[2 * e] - m1 - xh[2 * e] * m2);
+              const float b2 = rs * (dxh[2 * e + 1] - m1 - xh[2 * e + 1] * m2);
               w[e] = pack_bf16x2(a, b2);
               dbt[2 * e] += bf16_bits_to_float(w[e] & 0xffffu);
               dbt[2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
@@ -461,7 +534,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
         // the first kDepth - 1 batches are in flight while the dZ slot of this tile is still being read
 #pragma unroll
         for (int b = 0; b < kDepth - 1; ++b) issue(b, b);
-        fetch_idx(tile + gridDim.x, (t_local & 1) ^ 1);
+        // next tile: gather rows and rstd (row range from the ring: no dependent global load); ring refill 15 tiles ahead
+        int idx_next = 0;
+        float rstd_next = 0.f;
+        if (lt < kTile && tile + (int)gridDim.x < p.n_tiles) {
+          const int2 rn = trs_s[(t_local + 1) & 15];
+          if (lt < rn.y) {
+            if (p.dy_b16) idx_next = p.b_idx ? p.b_idx[(int64_t)rn.x + lt] : rn.x + lt;
+            rstd_next = p.rstd[(int64_t)rn.x + lt];
+          }
+        }
+        const bool refill = lt == kTile && (int64_t)tile + 15 * (int64_t)gridDim.x < p.n_tiles;
+        int2 rc_refill = make_int2(0, 0);
+        if (refill) rc_refill = tile_range(tile + 15 * gridDim.x);
         mbar_wait(z_empty(zs), ((t_local >> 1) & 1) ^ 1);
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L1: may write
 #pragma unroll
@@ -470,6 +555,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
           compute(b, b % kDepth);
           if (lt == 0) trace_ev(p.trace, 0, tn);  // Lb: one batch of rows done
         }
+        if (lt < kTile) {
+          idx_s[((t_local & 1) ^ 1) * kTile + lt] = idx_next;
+          rstd_s[((t_local & 1) ^ 1) * kTile + lt] = rstd_next;
+        }
+        if (refill) trs_s[(t_local + 15) & 15] = rc_refill;
         fence_proxy_async();
         named_bar_sync(2, kHeadThreads);
         if (lt == 0) trace_ev(p.trace, 0, tn);  // L2: top dZ written
@@ -607,6 +697,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
       int cnt;
       tile_rows(p.tile_row_start, p.M, tile, row0, cnt);
       if (lead) {
+        // the next tile's images into L2 (the epilogue's direct loads of the gradient image, the bulk loads of the rings)
+        const int nt = tile + gridDim.x;
+        if (nt < p.n_tiles) {
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.dz0) + (size_t)nt * kImg, kImg);
+          for (int b = 0; b < nblk; ++b) {
+            if (p.x_is_img[b]) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.x[b]) + (size_t)nt * kImg, kImg);
+            if (p.sink[b] == SINK_ADD_IMG && p.img_src[b])
+              bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.img_src[b]) + (size_t)nt * kImg, kImg);
+            if (p.sink[b] == SINK_ADD_F32 && p.f32_src[b]) {
+              const int64_t r0n = p.tile_row_start ? (int64_t)p.tile_row_start[nt] : (int64_t)nt * kTile;
+              const int64_t nn = p.tile_row_start ? (int64_t)(p.tile_row_start[nt + 1] - p.tile_row_start[nt])
+                                                  : min((int64_t)kTile, p.M - r0n);
+              if (nn > 0) bulk_prefetch_l2(p.f32_src[b] + r0n * 128, (uint32_t)nn * 512u);
+            }
+          }
+        }
         const uint32_t zs = t_local % kZ;
         mbar_wait(z_empty(zs), ((t_local / kZ) & 1) ^ 1);
         mbar_arrive_expect_tx(z_full(zs), kImg);
@@ -694,9 +800,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
           fence_proxy_async();
           tc_fence_after();
           const uint32_t d_w = tmem + 128u * (1 + b);
-          for (int ks = 0; ks < 8; ++ks)
-            umma(d_w, desc_mnmajor(x_slot(xs), (uint32_t)kTileB, ks), desc_mnmajor(z_slot(zs), (uint32_t)kTileB, ks),
-                 idesc_mn, (t_local | ks) != 0);
+          {
+            const uint32_t a_lo = mndesc_lo(x_slot(xs), (uint32_t)kTileB), b_lo = mndesc_lo(z_slot(zs), (uint32_t)kTileB);
+            umma_lo(d_w, a_lo, b_lo, idesc_mn, t_local != 0);
+#pragma unroll
+            for (int ks = 1; ks < 8; ++ks) umma_lo(d_w, a_lo + 128 * ks, b_lo + 128 * ks, idesc_mn, true);
+          }
           umma_commit(x_empty(xs));
           ++xc;
         };
@@ -711,8 +820,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
             const uint32_t ws = wc % kW;
             mbar_wait(w_full(ws), (wc / kW) & 1);
             tc_fence_after();
-            for (int k = 0; k < 4; ++k)
-              umma(tmem, desc_kmajor(z_slot(zs) + kb * kTileB, k), desc_kmajor(w_slot(ws), k), idesc_k, (kb | k) != 0);
+            const uint32_t a_lo = kdesc_lo(z_slot(zs) + kb * kTileB), b_lo = kdesc_lo(w_slot(ws));
+            umma_lo(tmem, a_lo, b_lo, idesc_k, kb != 0);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) umma_lo(tmem, a_lo + 2 * k, b_lo + 2 * k, idesc_k, true);
             umma_commit(w_empty(ws));
           }
           umma_commit(acc_full);

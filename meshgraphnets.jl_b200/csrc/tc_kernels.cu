@@ -306,10 +306,10 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
             ++it;
             fence_proxy_async();
             tc_fence_after();
-            const uint32_t a_tile = l == 0 ? s_ring + sa * kTileB : s_h + kb * kTileB;
-            const uint32_t b_tile = s_ring + sw * kTileB;
-            for (int k = 0; k < ksteps; ++k)
-              umma(tmem, desc_kmajor(a_tile, k), desc_kmajor(b_tile, k), idesc, (kb | k) != 0);
+            const uint32_t a_lo = kdesc_lo(l == 0 ? s_ring + sa * kTileB : s_h + kb * kTileB);
+            const uint32_t b_lo = kdesc_lo(s_ring + sw * kTileB);
+            umma_lo(tmem, a_lo, b_lo, idesc, kb != 0);
+            for (int k = 1; k < ksteps; ++k) umma_lo(tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, true);
             umma_commit(empty_bar(sw));
             if (l == 0) umma_commit(empty_bar(sa));
           }

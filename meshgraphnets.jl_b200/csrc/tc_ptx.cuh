@@ -65,6 +65,13 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Register reallocation between warpgroups (setmaxnreg): every warp of a warpgroup (4 consecutive warps) must execute
+// the same call.  N: multiple of 8 in [24, 256].
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ---- copies -------------------------------------------------------------------------------------
 // 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (UBLKCP).
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -76,6 +83,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                : "memory");
+}
+// Asks the TMA unit to bring `bytes` (multiple of 16, 16-byte aligned) into L2: no destination, no completion to wait for.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -134,6 +145,28 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t b
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+// The same with the descriptors split into 32-bit halves.  Only the start-address field (low 14 bits of the low word,
+// in 16-byte units) changes between the MMAs of a K loop, so the issuing thread builds a descriptor ONCE per operand tile
+// and adds a constant per step - the single thread that issues the MMAs is latency bound on exactly this arithmetic
+// (a descriptor rebuilt from the address costs ~8 dependent integer operations per operand and MMA, more than the
+// 64 cycles the tensor pipe needs for the MMA itself).  Shared-memory addresses are < 256 KB: the field cannot overflow.
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t kdesc_lo(uint32_t tile_addr) {      // K-major T128 tile; K step: + 2 (32 bytes)
+  return ((tile_addr >> 4) & 0x3FFFu) | ((16u >> 4) << 16);
+}
+__device__ __forceinline__ uint32_t mndesc_lo(uint32_t tile_addr, uint32_t slab_bytes) {   // MN-major; K step: + 128 (2048 bytes)
+  return ((tile_addr >> 4) & 0x3FFFu) | (((slab_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(idesc), "r"((uint32_t)accumulate), "r"(kDescHi)
       : "memory");
 }
 // All MMAs issued so far by this thread arrive on the mbarrier when they complete
