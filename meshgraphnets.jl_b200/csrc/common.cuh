@@ -79,6 +79,8 @@ struct TuneKnobs {
   int fwd_epi_warps = 8;   // MGN_FWD_EPI_WARPS=4 selects the one-thread-per-row epilogue
   int fwd_stagger_ns = 0;  // MGN_FWD_STAGGER_NS
   int fwd_deep_ring = 1;   // MGN_FWD_DEEP_RING=0 disables the deep-ring variant for small graphs
+  int fwd_persist = 1;     // inference pass of a graph with no more tiles than SMs as ONE persistent cooperative launch:
+                           // MGN_FWD_PERSIST=0 never, 1 unless the call is being captured into a CUDA graph, 2 always
   int reduce_lane = 1;     // MGN_REDUCE_LANE=0: reduce the weight-gradient partials inline on the caller's stream
   int pdl = 0;             // MGN_PDL=1: programmatic dependent launch between the library's kernels (measured: no gain
                            // inside a CUDA graph, -3 % on the 32-window step; kept as an opt-in for eager callers)

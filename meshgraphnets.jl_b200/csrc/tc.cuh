@@ -66,7 +66,9 @@ cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat
 enum InMode { IN_RAW = 0, IN_PLAIN = 1, IN_CONCAT2 = 2, IN_GATHER3 = 3 };
 enum FinMode { FIN_LN = 0, FIN_LN_RESID = 1, FIN_LN_RESID_AGG = 2, FIN_LINEAR = 3 };
 
-struct FwdParams {
+// Everything a forward launch needs except the two feature recipes (which only the encoders / the decoder read, once, in
+// their prologue): the persistent kernel keeps one FwdCore per stage in kernel-parameter space.
+struct FwdCore {
   // tiling
   int n_tiles;
   int64_t M;                          // rows
@@ -78,9 +80,8 @@ struct FwdParams {
   const __nv_bfloat16 *x0, *x1, *x2;  // row-major [rows][128] bf16
   const __nv_bfloat16* x2_img;        // IN_GATHER3: the third segment as tile images [tile][2][16 KB] (bulk copies)
   const int32_t *idx0, *idx1;         // IN_GATHER3: rows of x0 for K-blocks {0,1} / {2,3}
-  FeatRecipe feat;                    // IN_RAW: the raw fp32 features as a recipe (features.cuh): normalise + concat on the fly
   const int32_t* raw_idx;             // IN_RAW: optional row gather (CSR perm)
-  int raw_F;                          // == feat.F
+  int raw_F;                          // == FwdParams::feat.F
   // layers
   int n_layers;
   int nkb[kMaxLayers];                // K-blocks (64 wide) of each layer
@@ -100,8 +101,7 @@ struct FwdParams {
   __nv_bfloat16* agg_bf16;            // [nodes][128]
   float* out;                         // FIN_LINEAR: [rows][out_dim]
   int out_dim;
-  FeatRecipe out_feat;                // FIN_LINEAR: inverse_data per output column (n == 0: none) ...
-  const float* val_mask;              // ... and `.* val_mask` [rows][out_dim] (nullable)   <- src/solve.jl:205-218
+  const float* val_mask;              // FIN_LINEAR: `.* val_mask` [rows][out_dim] (nullable)   <- src/solve.jl:218
   // training saves (nullptr when not training)
   __nv_bfloat16* save_h[kMaxLayers - 1];  // image [tile][2 tiles]
   __nv_bfloat16* save_xhat;               // image [tile][2 tiles]
@@ -112,8 +112,24 @@ struct FwdParams {
   int deep_ring;                          // allow the deep-ring variant when the graph has no more tiles than SMs
   int pdl;                                // programmatic dependent launch (common.cuh)
 };
+struct FwdParams : FwdCore {
+  FeatRecipe feat;                    // IN_RAW: the raw fp32 features as a recipe (features.cuh): normalise + concat on the fly
+  FeatRecipe out_feat;                // FIN_LINEAR: inverse_data per output column (n == 0: none)   <- src/solve.jl:205-210
+};
 
 cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st);
+
+// Persistent forward pass (graphs with no more tiles than SMs): every MLP of the pass is a stage of ONE cooperative launch.
+constexpr int kMaxStages = 36;   // 3 + 2 * mps: mps <= 16
+struct PersistParams {
+  int n_stages;
+  unsigned int* sync;            // grid-barrier counter, zeroed on the stream before the launch
+  FeatRecipe feat[3];            // node encoder input, edge encoder input, decoder output
+  FwdCore stage[kMaxStages];     // stage 0: node encoder, 1: edge encoder, then (edge, node) per MP step, last: decoder
+};
+// True when the pass can run persistently on the current device (tile counts, stage count).
+bool forward_persist_ok(int max_tiles, int n_stages);
+cudaError_t mlp_forward_persist_tc(const PersistParams& pp, int max_tiles, cudaStream_t st);
 // Debug: the `skip`-th next launch of kernel family `kernel` (0 forward, 1 backward chain, 2 backward input)
 // records timestamps into d_buf [4 roles][kTraceLen] (u64 nanoseconds).
 constexpr int kTraceLen = 512;

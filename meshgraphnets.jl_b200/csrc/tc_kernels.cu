@@ -88,7 +88,7 @@ pack_kernel(const PackTile* __restrict__ tiles, const float* __restrict__ params
 // ---------------------------------------------------------------------------------------------------
 // Fused MLP forward
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_rows(const FwdParams& p, int tile, int64_t& row0, int& cnt) {
+__device__ __forceinline__ void tile_rows(const FwdCore& p, int tile, int64_t& row0, int& cnt) {
   if (p.tile_row_start) {
     row0 = p.tile_row_start[tile];
     cnt = p.tile_row_start[tile + 1] - (int)row0;
@@ -102,8 +102,42 @@ __device__ __forceinline__ void tile_rows(const FwdParams& p, int tile, int64_t&
 // the gather instructions of a tile are issued four times faster - what bounds the latency of a single tile).
 // kResImg: the residual input is the bf16 tile image of the latent itself (edge MLPs) - all its rows are requested at
 // once as raw 16-byte chunks (same register budget as the double-buffered fp32 rows of the node MLPs).
+// Rows of the gather sources for this lane's tile rows (lane + 32 * (pw * RPW + rr)).
+template <int RPW>
+__device__ __forceinline__ void gather_rows(const FwdCore& p, int64_t row0, int cnt, int lane, int pw, int32_t (&src0)[RPW],
+                                            int32_t (&src1)[RPW]) {
+#pragma unroll
+  for (int rr = 0; rr < RPW; ++rr) {
+    const int r = lane + 32 * (pw * RPW + rr);
+    const bool ok = r < cnt;
+    const int32_t* i0 = p.in_mode == IN_RAW ? p.raw_idx : (p.in_mode == IN_GATHER3 ? p.idx0 : nullptr);
+    const int32_t* i1 = p.in_mode == IN_GATHER3 ? p.idx1 : nullptr;
+    src0[rr] = ok ? (i0 ? i0[row0 + r] : (int32_t)(row0 + r)) : 0;
+    src1[rr] = ok ? (i1 ? i1[row0 + r] : (int32_t)(row0 + r)) : 0;
+  }
+}
+
+// Per-thread state that survives from one stage of the persistent kernel to the next (registers): the mbarrier phases run
+// on across stages (no re-initialisation), and the producer warps fetch the row range and the gather rows of their next
+// tile - static graph data - BEFORE the grid barrier, while the other roles still work on the current stage.
+template <int RPW>
+struct StageCarry {
+  uint32_t it = 0;        // producer / MMA thread: ring item counter
+  uint32_t par = 0;       // MMA thread: epi_done parity; epilogue threads: acc_full parity
+  bool started = false;   // MMA thread: an accumulator round has been issued (the next one waits for epi_done)
+  bool have = false;      // producer: row0 / cnt / src* below describe the CTA's first tile of the coming stage
+  int32_t row0 = 0, cnt = 0;
+  int32_t src0[RPW] = {}, src1[RPW] = {};
+};
+
+// The body of one launch / one stage of the persistent kernel.  `smem` is the 1024-byte aligned shared-memory base, `tmem`
+// the CTA's 128 accumulator columns; `later_stage`: the mbarriers are live from a previous stage (see StageCarry); `next`:
+// the parameters of the coming stage (nullptr: none).
+// Ends with a CTA-wide barrier: every role is done and every store of the CTA has been issued (bulk stores completed).
 template <int EW, int RING, int NP, bool kResImg = false>
-__global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 1) mlp_fwd_kernel(const FwdParams p) {
+__device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& feat, const FeatRecipe& out_feat, uint8_t* smem,
+                                         const uint32_t tmem, const bool later_stage, StageCarry<4 / NP>& cy,
+                                         const FwdCore* next) {
   using L_ = Lay<RING>;
   constexpr int kRing = RING;
   constexpr uint32_t kSmemRing = L_::kRing, kSmemH = L_::kH, kSmemBias = L_::kBias, kSmemLn = L_::kLn, kSmemRp = L_::kRp,
@@ -114,8 +148,6 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
   constexpr int kHalves = EW / 4;      // threads per tile row
   constexpr int kWarpP = EW, kWarpM = EW + NP;
   constexpr int RPW = 4 / NP;          // 32-row groups staged by one producer warp
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t s_base = smem_u32(smem);
   const uint32_t s_ring = s_base + kSmemRing, s_h = s_base + kSmemH;
   float* bias_s = reinterpret_cast<float*>(smem + kSmemBias);
@@ -127,15 +159,13 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (kRing + s); };
   const uint32_t acc_full = bar0 + 8u * (2 * kRing), epi_done = bar0 + 8u * (2 * kRing + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmemTmem);
+  (void)kSmemTmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = p.n_layers;
 
-  // ---- one-time setup.  Everything that touches no global memory first (barriers, TMEM allocation): with programmatic
-  //      dependent launch this part overlaps the tail of the previous kernel; pdl_wait() then orders every global access.
-  pdl_trigger();
-  if (tid == 0) {
+  // ---- setup of a launch / stage: barriers, per-MLP tables
+  if (tid == 0 && !later_stage) {
     for (int s = 0; s < kRing; ++s) {
       mbar_init(full_bar(s), 32 * NP);
       mbar_init(empty_bar(s), 1);
@@ -144,10 +174,8 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
     mbar_init(epi_done, kEpi);
     fence_mbar_init();
   }
-  if (warp == kWarpM) tmem_alloc(smem_u32(tmem_slot), 128);
-  pdl_wait();
-  if (p.in_mode == IN_RAW) feat_table(p.feat, ftab, tid, kThreads);
-  if (p.fin_mode == FIN_LINEAR && p.out_feat.n > 0) feat_table(p.out_feat, otab, tid, kThreads);
+  if (p.in_mode == IN_RAW) feat_table(feat, ftab, tid, kThreads);
+  if (p.fin_mode == FIN_LINEAR && out_feat.n > 0) feat_table(out_feat, otab, tid, kThreads);
   for (int i = tid; i < L * 128; i += kThreads) {
     const int l = i >> 7, c = i & 127;
     const int nout = (l == L - 1) ? p.n_out_last : 128;
@@ -158,11 +186,10 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
 
   if (warp >= kWarpP && warp < kWarpM) {
     // ================================ producer ================================
-    uint32_t it = 0;
+    uint32_t it = cy.it;
     int tn = 0;
     const int pw = warp - kWarpP;
     const bool lead = lane == 0 && pw == 0;  // issues the bulk copies
@@ -175,18 +202,20 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       int64_t row0;
       int cnt;
-      tile_rows(p, tile, row0, cnt);
       // source rows of this lane's 4 tile rows, for both gather index vectors: all index loads of the tile
       // are issued together, so no K-block waits on a dependent index load
       int32_t src0[RPW], src1[RPW];
+      if (cy.have && tile == (int)blockIdx.x) {   // fetched before the grid barrier that opened this stage
+        row0 = cy.row0;
+        cnt = cy.cnt;
 #pragma unroll
-      for (int rr = 0; rr < RPW; ++rr) {
-        const int r = lane + 32 * (pw * RPW + rr);
-        const bool ok = r < cnt;
-        const int32_t* i0 = p.in_mode == IN_RAW ? p.raw_idx : (p.in_mode == IN_GATHER3 ? p.idx0 : nullptr);
-        const int32_t* i1 = p.in_mode == IN_GATHER3 ? p.idx1 : nullptr;
-        src0[rr] = ok ? (i0 ? i0[row0 + r] : (int32_t)(row0 + r)) : 0;
-        src1[rr] = ok ? (i1 ? i1[row0 + r] : (int32_t)(row0 + r)) : 0;
+        for (int rr = 0; rr < RPW; ++rr) {
+          src0[rr] = cy.src0[rr];
+          src1[rr] = cy.src1[rr];
+        }
+      } else {
+        tile_rows(p, tile, row0, cnt);
+        gather_rows<RPW>(p, row0, cnt, lane, pw, src0, src1);
       }
       for (int l = 0; l < L; ++l) {
         for (int kb = 0; kb < p.nkb[l]; ++kb) {
@@ -274,11 +303,22 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
         }
       }
     }
+    cy.it = it;
+    cy.have = false;
+    if (next != nullptr && (int)blockIdx.x < next->n_tiles) {   // static data of the coming stage, ahead of the grid barrier
+      int64_t r0;
+      int n;
+      tile_rows(*next, blockIdx.x, r0, n);
+      cy.row0 = (int32_t)r0;
+      cy.cnt = n;
+      gather_rows<RPW>(*next, r0, n, lane, pw, cy.src0, cy.src1);
+      cy.have = true;
+    }
   } else if (warp == kWarpM) {
     // ================================ MMA issue ================================
     if (lane == 0) {
-      uint32_t it = 0, epi_par = 0;
-      bool first = true;
+      uint32_t it = cy.it, epi_par = cy.par;
+      bool first = !cy.started;
       int tn = 0;
       const uint32_t idesc_full = umma_idesc(128, 128, false, false);
       const uint32_t idesc_last = p.fin_mode == FIN_LINEAR ? umma_idesc(128, 16, false, false) : idesc_full;
@@ -317,10 +357,13 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
           trace_ev(p.trace, 1, tn);  // M2: layer issued (operands were there)
         }
       }
+      cy.it = it;
+      cy.par = epi_par;
+      cy.started = !first;
     }
   } else {
     // ================================ epilogue (thread == (row, column half)) ================================
-    uint32_t acc_par = 0;
+    uint32_t acc_par = cy.par;
     bool store_pending = false;
     int tn = 0;
     const int row = tid & 127, half = tid >> 7;  // half == 0 when EW == 4
@@ -344,7 +387,7 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
           tc_fence_before();
           mbar_arrive(epi_done);
           if (half == 0 && row < cnt) {
-            const bool fused_out = p.out_feat.n > 0;
+            const bool fused_out = out_feat.n > 0;
             for (int j = 0; j < p.out_dim; ++j) {
               float y = v[j] + bias_s[l * 128 + j];
               if (fused_out) y = out_eval(otab[j], y);                                   // inverse_data (src/solve.jl:205-210)
@@ -391,9 +434,9 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
             if constexpr (kResImg) {
               rq[U * k + u] = make_uint4(0u, 0u, 0u, 0u);
               if (resid && i < cnt)  // an L2 hit: the producer staged this very tile as an operand a few microseconds ago
-                rq[U * k + u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.lat_img_in) +
-                                                                (size_t)tile * 2 * kTileB + (cc >> 3) * kTileB +
-                                                                t128_off(i, cc & 7));
+                rq[U * k + u] = ld_global_cg_v4(reinterpret_cast<const uint8_t*>(p.lat_img_in) + (size_t)tile * 2 * kTileB +
+                                                (cc >> 3) * kTileB + t128_off(i, cc & 7));   // L2: the image is written by
+                                                                                             // bulk stores, which L1 never sees
             } else {
               r0[U * h + u] = make_float4(0.f, 0.f, 0.f, 0.f);
               r1[U * h + u] = r0[U * h + u];
@@ -667,10 +710,77 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 
       }
     }
     if (tid == 0 && store_pending) bulk_wait0();
+    cy.par = acc_par;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kWarpM) tmem_dealloc(tmem, 128);
+}
+
+// One launch = one MLP.
+template <int EW, int RING, int NP, bool kResImg = false>
+__global__ void __launch_bounds__(32 * (EW + NP + 1), RING == kRingShared ? 2 : 1) mlp_fwd_kernel(const __grid_constant__ FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Lay<RING>::kTmem);
+  const int warp = threadIdx.x >> 5;
+  // no global memory access before pdl_wait(): with programmatic dependent launch the TMEM allocation overlaps the tail
+  // of the previous kernel
+  pdl_trigger();
+  if (warp == EW + NP) tmem_alloc(smem_u32(tmem_slot), 128);
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  StageCarry<4 / NP> cy;
+  fwd_body<EW, RING, NP, kResImg>(p, p.feat, p.out_feat, smem, tmem, false, cy, nullptr);
+  if (warp == EW + NP) tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Persistent forward pass for graphs with no more tiles than SMs: ONE cooperative launch runs every MLP of the pass
+// (encoders, mps x (edge, node), decoder) as a stage, with a grid-wide barrier where a launch boundary used to be - a
+// stage of such a graph is one tile's dependency chain per CTA (10 - 12 us), and a third of an inference pass was the
+// launch gaps and kernel prologues between the stages.  The stages' parameters live in kernel-parameter space (a FwdCore
+// each, indexed by the stage: constant-bank loads); ring and accumulator barriers keep their phases across stages.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+  __syncthreads();   // every global write of the CTA happens-before thread 0's release below
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    unsigned int seen;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (clock64() - t0 > 4000000000LL) __trap();   // a CTA that never arrived: fail the launch instead of hanging
+    } while (seen < target);
+  }
+  __syncthreads();
+}
+
+template <int EW, int RING, int NP>
+__global__ void __launch_bounds__(32 * (EW + NP + 1), 1) mlp_fwd_persist_kernel(const __grid_constant__ PersistParams pp) {
+  using L_ = Lay<RING>;
+  constexpr int kThreads = 32 * (EW + NP + 1);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L_::kTmem);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == EW + NP) tmem_alloc(smem_u32(tmem_slot), 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  StageCarry<4 / NP> cy;
+  for (int si = 0; si < pp.n_stages; ++si) {
+    const FwdCore& p = pp.stage[si];   // kernel-parameter space, indexed: the fields stay constant-bank loads
+    const FeatRecipe& feat = pp.feat[si == 1 ? 1 : 0];
+    const FwdCore* next = si + 1 < pp.n_stages ? &pp.stage[si + 1] : nullptr;
+    if (p.lat_img_in != nullptr) fwd_body<EW, RING, NP, true>(p, feat, pp.feat[2], smem, tmem, si > 0, cy, next);
+    else fwd_body<EW, RING, NP, false>(p, feat, pp.feat[2], smem, tmem, si > 0, cy, next);
+    if (si + 1 < pp.n_stages) grid_barrier(pp.sync, (unsigned int)(si + 1) * gridDim.x);
+  }
+  if (warp == EW + NP) tmem_dealloc(tmem, 128);
 }
 
 }  // namespace
@@ -683,10 +793,10 @@ cudaError_t pack_weights(const ModelImages& im, const float* params, __nv_bfloat
 
 // Variant selection comes from the model handle (FwdParams::epi_warps / deep_ring / stagger_ns, frozen at
 // mgn_model_create); the opt-in shared-memory limits are set once per device.
-cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
-  if (p.n_tiles == 0) return cudaSuccess;
+// The opt-in shared-memory limits of every forward kernel, once per device.
+static cudaError_t configure_forward() {
   static PerDeviceOnce configured;
-  cudaError_t ce = configured.run([](int) {
+  return configured.run([](int) {
     cudaError_t e = cudaSuccess;
     auto set = [&](const void* f, uint32_t bytes) {
       if (e == cudaSuccess) e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -697,8 +807,14 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
     set((const void*)mlp_fwd_kernel<4, kRingShared, 1, true>, Lay<kRingShared>::kLaunch);
     set((const void*)mlp_fwd_kernel<8, kRingShared, 1, true>, Lay<kRingShared>::kLaunch);
     set((const void*)mlp_fwd_kernel<8, kRingDeep, 4, true>, Lay<kRingDeep>::kLaunch);
+    set((const void*)mlp_fwd_persist_kernel<8, kRingDeep, 4>, Lay<kRingDeep>::kLaunch);
     return e;
   });
+}
+
+cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
+  if (p.n_tiles == 0) return cudaSuccess;
+  cudaError_t ce = configure_forward();
   if (ce != cudaSuccess) return ce;
   const int n_sm = device_sm_count();
   const int grid = p.n_tiles < 2 * n_sm ? p.n_tiles : 2 * n_sm;
@@ -717,6 +833,29 @@ cudaError_t mlp_forward_tc(const FwdParams& p, cudaStream_t st) {
                : launch_kernel(pdl, mlp_fwd_kernel<8, kRingDeep, 4, false>, dim3(grid), dim3(32 * 13), Lay<kRingDeep>::kLaunch, st, q);
   return img ? launch_kernel(pdl, mlp_fwd_kernel<8, kRingShared, 1, true>, dim3(grid), dim3(32 * 10), Lay<kRingShared>::kLaunch, st, q)
              : launch_kernel(pdl, mlp_fwd_kernel<8, kRingShared, 1, false>, dim3(grid), dim3(32 * 10), Lay<kRingShared>::kLaunch, st, q);
+}
+
+bool forward_persist_ok(int max_tiles, int n_stages) {
+  return max_tiles > 0 && max_tiles <= device_sm_count() && n_stages <= kMaxStages;
+}
+
+cudaError_t mlp_forward_persist_tc(const PersistParams& pp, int max_tiles, cudaStream_t st) {
+  cudaError_t ce = configure_forward();
+  if (ce != cudaSuccess) return ce;
+  ce = cudaMemsetAsync(pp.sync, 0, sizeof(unsigned int), st);
+  if (ce != cudaSuccess) return ce;
+  ProfScope ps(TAG_TC_MLP_FWD, st);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(max_tiles);
+  cfg.blockDim = dim3(32 * 13);
+  cfg.dynamicSmemBytes = Lay<kRingDeep>::kLaunch;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;   // every CTA resident before any runs: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, mlp_fwd_persist_kernel<8, kRingDeep, 4>, pp);
 }
 
 }  // namespace tc
