@@ -374,6 +374,15 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
       int64_t row0;
       int cnt;
       tile_rows(p, tile, row0, cnt);
+      // tile-local CSR row pointer of the aggregation: requested now (two dependent loads), stored to shared memory in
+      // layer 0's epilogue - the wait for the first accumulator hides them
+      int rp_n0 = 0, rp_nn = 0, rp_raw = 0, rp_last = 0;
+      if (p.fin_mode == FIN_LN_RESID_AGG) {
+        rp_n0 = p.tile_node_start[tile];
+        rp_nn = p.tile_node_start[tile + 1] - rp_n0;
+        if (tid <= rp_nn) rp_raw = p.row_ptr[rp_n0 + tid];
+        if (tid == 0 && rp_nn == 128) rp_last = p.row_ptr[rp_n0 + 128];
+      }
       for (int l = 0; l < L; ++l) {
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E0: layer start
         mbar_wait(acc_full, acc_par);
@@ -400,22 +409,33 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
         // the shared activation tile is about to be overwritten: every thread must be done reading the
         // previous tile's copy-out / aggregation, and a pending bulk store must have read it
         // (layers > 0 of an inference pass: the tile's last reader was this layer's MMA, which has completed - no barrier)
-        if (l == 0 || p.save_h[0] != nullptr) {
+        // Two threads per row: the barrier stands in front of the first STORE into the tile (the accumulator is loaded and
+        // converted before it, off the wait for the bulk store's read of the tile); `pre_bar`: thread 0's part of it.
+        auto pre_bar = [&]() {
           if (tid == 0 && store_pending) {
             bulk_wait_read0();
             store_pending = false;
           }
-          named_bar_sync(1, kEpi);
-        }
-        if (l == 0 && p.fin_mode == FIN_LN_RESID_AGG) {
-          // tile-local CSR row pointer -> shared memory (read by the aggregation after two more barriers)
-          const int n0 = p.tile_node_start[tile], nn = p.tile_node_start[tile + 1] - n0;
-          if (tid <= nn) rp_s[tid] = p.row_ptr[n0 + tid] - (int)row0;
-          if (tid == 0) {
-            if (nn == 128) rp_s[128] = p.row_ptr[n0 + 128] - (int)row0;
-            rp_s[130] = n0;
-            rp_s[131] = nn;
+        };
+        auto post_bar = [&]() {
+          if (l == 0 && p.fin_mode == FIN_LN_RESID_AGG) {
+            // tile-local CSR row pointer -> shared memory (read by the aggregation after two more barriers); the values
+            // were requested at the top of the tile
+            if (tid <= rp_nn) rp_s[tid] = rp_raw - (int)row0;
+            if (tid == 0) {
+              if (rp_nn == 128) rp_s[128] = rp_last - (int)row0;
+              rp_s[130] = rp_n0;
+              rp_s[131] = rp_nn;
+            }
           }
+        };
+        const bool need_bar = l == 0 || p.save_h[0] != nullptr;
+        if (kHalves == 1 || last) {   // (the LayerNorm layer synchronises on its statistics exchange anyway)
+          if (need_bar) {
+            pre_bar();
+            if (kHalves == 1 || !last) named_bar_sync(1, kEpi);
+          }
+          if (kHalves == 1) post_bar();
         }
         // residual rows of the first copy-out batch: issued now so that their latency hides behind the LayerNorm
         // residual rows are fetched 4 per thread at a time into one half of r0/r1 while the other half is consumed
@@ -474,6 +494,13 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
                 w[2 * q] = pack_bf16x2_relu(__uint_as_float(r[4 * q]) + b4.x, __uint_as_float(r[4 * q + 1]) + b4.y);
                 w[2 * q + 1] = pack_bf16x2_relu(__uint_as_float(r[4 * q + 2]) + b4.z, __uint_as_float(r[4 * q + 3]) + b4.w);
               }
+              if (cc2 == 0) {
+                if (need_bar) {
+                  pre_bar();
+                  named_bar_sync(1, kEpi);
+                }
+                post_bar();
+              }
               store_chunk(c_lo + cc2, w);
             }
           } else {
@@ -503,7 +530,8 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
               }
             }
             stat_s[half * 128 + row] = make_float2(s, q);
-            named_bar_sync(1, kEpi);
+            named_bar_sync(1, kEpi);   // also the barrier in front of the stores into the tile (thread 0 waited in pre_bar)
+            post_bar();
             const float2 a = stat_s[row], b = stat_s[128 + row];
             s = a.x + b.x;
             q = a.y + b.y;
