@@ -124,6 +124,7 @@ constexpr int kMaxStages = 36;   // 3 + 2 * mps: mps <= 16
 struct PersistParams {
   int n_stages;
   unsigned int* sync;            // grid-barrier counter, zeroed on the stream before the launch
+  unsigned long long* dbg;       // debug build only: CTA 0 stamps %globaltimer at [3 * stage + {0: top, 1: body done, 2: barrier passed}]
   FeatRecipe feat[3];            // node encoder input, edge encoder input, decoder output
   FwdCore stage[kMaxStages];     // stage 0: node encoder, 1: edge encoder, then (edge, node) per MP step, last: decoder
 };

@@ -804,9 +804,19 @@ __global__ void __launch_bounds__(32 * (EW + NP + 1), 1) mlp_fwd_persist_kernel(
     const FwdCore& p = pp.stage[si];   // kernel-parameter space, indexed: the fields stay constant-bank loads
     const FeatRecipe& feat = pp.feat[si == 1 ? 1 : 0];
     const FwdCore* next = si + 1 < pp.n_stages ? &pp.stage[si + 1] : nullptr;
+#ifdef MGN_ENABLE_TRACE
+    const bool stamp = pp.dbg != nullptr && blockIdx.x == 0 && tid == 0;
+    if (stamp) pp.dbg[3 * si] = globaltimer_ns();
+#endif
     if (p.lat_img_in != nullptr) fwd_body<EW, RING, NP, true>(p, feat, pp.feat[2], smem, tmem, si > 0, cy, next);
     else fwd_body<EW, RING, NP, false>(p, feat, pp.feat[2], smem, tmem, si > 0, cy, next);
+#ifdef MGN_ENABLE_TRACE
+    if (stamp) pp.dbg[3 * si + 1] = globaltimer_ns();
+#endif
     if (si + 1 < pp.n_stages) grid_barrier(pp.sync, (unsigned int)(si + 1) * gridDim.x);
+#ifdef MGN_ENABLE_TRACE
+    if (stamp) pp.dbg[3 * si + 2] = globaltimer_ns();
+#endif
   }
   if (warp == EW + NP) tmem_dealloc(tmem, 128);
 }
@@ -873,6 +883,8 @@ cudaError_t mlp_forward_persist_tc(const PersistParams& pp, int max_tiles, cudaS
   ce = cudaMemsetAsync(pp.sync, 0, sizeof(unsigned int), st);
   if (ce != cudaSuccess) return ce;
   ProfScope ps(TAG_TC_MLP_FWD, st);
+  PersistParams q = pp;
+  q.dbg = take_trace(0);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(max_tiles);
   cfg.blockDim = dim3(32 * 13);
@@ -883,7 +895,7 @@ cudaError_t mlp_forward_persist_tc(const PersistParams& pp, int max_tiles, cudaS
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, mlp_fwd_persist_kernel<8, kRingDeep, 4>, pp);
+  return cudaLaunchKernelEx(&cfg, mlp_fwd_persist_kernel<8, kRingDeep, 4>, q);
 }
 
 }  // namespace tc
