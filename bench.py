@@ -51,7 +51,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default=os.environ.get("MGN_BENCH_MODE", "bf16"), choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("MGN_BENCH_BATCH", "32")),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("MGN_BENCH_BATCH", "64")),
                     help="time windows (graphs) per step per GPU; the reference is batch 1 (reported as `batch1`)")
     ap.add_argument("--no-graph", action="store_true", help="do not replay the step as a CUDA graph")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -119,6 +119,9 @@ def roofline_and_launches(args, pkg, model, mgn, E, B, dev, step_fn=None, n_node
     else:
         fams = algorithmic_work(E, n_nodes, D, L, MPS, 9, 3, 2)
     traffic = ncu_traffic()
+    if traffic.get("_windows"):   # captured on a different window count: DRAM traffic is proportional to the rows
+        scale = float(B) / float(traffic["_windows"])
+        traffic = {k: (v * scale if isinstance(v, (int, float)) and not k.startswith("_") else v) for k, v in traffic.items()}
     reps = 3
     rows = []
     for name, (flops, nbytes) in fams.items():
