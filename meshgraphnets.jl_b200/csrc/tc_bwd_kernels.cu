@@ -36,6 +36,26 @@ __device__ __forceinline__ void tile_rows(const int32_t* trs, int64_t M, int til
 
 __device__ __forceinline__ float bf16_bits_to_float(uint32_t bits16) { return __uint_as_float(bits16 << 16); }
 
+// A warp's 32 rows x 32 fp32 columns of a TMEM accumulator (thread == row: v[32]) -> global rows of 128 floats, through 4 KB of
+// warp-private shared memory `scr` (16-byte chunks XOR-swizzled by the row: conflict free both ways).  Stored straight from the
+// registers every instruction would touch 32 different lines (one 16-byte piece of each lane's row); read back transposed, eight
+// lanes write the 128 contiguous bytes of a row: 4 lines per instruction.  `g`: element (first row of the warp, first column).
+__device__ __forceinline__ void store_acc_chunk(uint32_t scr, const float (&v)[32], float* g, int lane) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    st_shared_v4(scr + (uint32_t)lane * 128u + (uint32_t)((q ^ (lane & 7)) << 4), __float_as_uint(v[4 * q]),
+                 __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]), __float_as_uint(v[4 * q + 3]));
+  __syncwarp();
+  const int ch = lane & 7, sub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = 4 * i + sub;
+    const uint4 x = ld_shared_v4(scr + (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4));
+    *reinterpret_cast<uint4*>(g + (size_t)r * 128 + ch * 4) = x;
+  }
+  __syncwarp();
+}
+
 // ======================================================================================================
 // Chain kernel
 // ======================================================================================================
@@ -337,14 +357,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
     // ---- weight-gradient partials: TMEM -> global, once per launch
     mbar_wait(done_bar, 0);
     tc_fence_after();
+    named_bar_sync(1, kEpiThreads);   // thread 0 has waited for the last dZ bulk store's read: the dZ slots are free
     for (int j = 0; j < ns; ++j) {
 #pragma unroll 1
       for (int c = 2 * half; c < 2 * half + 2; ++c) {
         float v[32];
         tmem_ld32(t_lane + 128u * (1 + j) + c * 32, v);
-        float4* dst = reinterpret_cast<float4*>(my_partial + (size_t)j * 16384 + (size_t)row * 128 + c * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        // staging: 4 KB per epilogue warp in dZ slot 3 (every MMA is done; the bias-gradient reduction below uses slot 2,
+        // the head's final reduction slot 0 or 1)
+        store_acc_chunk(s_base + kSmemZ + 3u * kImg + (uint32_t)warp * 4096u, v,
+                        my_partial + (size_t)j * 16384 + (size_t)((warp & 3) * 32) * 128 + c * 32, lane);
       }
     }
     // bias gradients: [16 row groups][3 steps][128] through an epilogue dZ slot (all MMAs and the last dZ bulk
@@ -423,11 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
       if (lt < 16 && blockIdx.x + lt * (int)gridDim.x < p.n_tiles) trs_s[lt] = tile_range(blockIdx.x + lt * gridDim.x);
       named_bar_sync(2, kHeadThreads);
       // Batches of 32 rows (2 per thread: i = 32 b + 2 rg + u) flow through a register pipeline kDepth batches deep: the
-      // loads of batch b + kDepth - 1 are issued before batch b is computed, so that many batches' worth of bytes are in
-      // flight per thread.  In the image form everything arrives as 16-byte bf16 chunks kept as raw bits (edge MLPs: the
-      // gradient image, the gathered d_agg row, xhat: 13 registers per row), which pays for the third stage; the fp32
-      // form (node MLPs, encoders: 8 + 4 + 1 registers per row, no gather) stays double buffered.
-      constexpr int kDepth = kDyImg ? 3 : 2;
+      // loads of batch b + kDepth - 1 are issued before batch b is computed.  In the image form everything arrives as
+      // 16-byte bf16 chunks kept as raw bits (edge MLPs: the gradient image, the gathered d_agg row, xhat: 12 registers
+      // per row).  Two stages: a third one (round 2a) measured the same on the device - the head does not wait for want of
+      // bytes in flight - and pushed the accumulators into local memory.
+      constexpr int kDepth = 2;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++t_local) {
         const int2 rc = trs_s[t_local & 15];
         const int64_t row0 = rc.x;
@@ -999,14 +1021,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_input_kernel(const InputP
     if (tid == 0 && stage_store_pending) bulk_wait0();
     mbar_wait(done_bar, 0);
     tc_fence_after();
+    named_bar_sync(1, kEpi);   // the staging tile is free: its last bulk store has completed, its last reader is past its sink
     for (int b = 0; b < nblk; ++b) {
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; ++c) {
         float v[32];
         tmem_ld32(t_lane + 128u * (1 + b) + c * 32, v);
-        float4* dst = reinterpret_cast<float4*>(my_partial + (size_t)b * 16384 + (size_t)row * 128 + c * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        store_acc_chunk(s_stage + (uint32_t)warp * 4096u, v,
+                        my_partial + (size_t)b * 16384 + (size_t)((warp & 3) * 32) * 128 + c * 32, lane);
       }
     }
   }
