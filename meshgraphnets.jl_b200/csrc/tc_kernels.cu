@@ -7,10 +7,12 @@
 //     the pre-swizzled bf16 weight images with 1-D bulk (TMA) copies through a 4-slot ring;
 //   * one thread of the MMA warp issues tcgen05.mma (M=128, N=128, K=16) into a 128-column fp32
 //     TMEM accumulator;
-//   * four epilogue warps (thread == row) read TMEM, add bias, apply ReLU and write the next
+//   * eight epilogue warps (two threads per tile row) read TMEM, add bias, apply ReLU and write the next
 //     layer's A operand straight back into shared memory as bf16 - hidden activations never leave
 //     the SM; the last layer's epilogue does LayerNorm, the residual add and the deterministic
 //     CSR segmented sum (a11) from shared memory, so the per-edge message never touches HBM.
+// mlp_fwd_persist_kernel: the same body for every MLP of an inference pass of a small graph, as stages of one
+// cooperative launch with a grid barrier between them.
 // Two CTAs are resident per SM (<= 113 KB smem, 128 TMEM columns each) so one CTA's epilogue
 // overlaps the other's MMAs.
 #include "tc.cuh"
