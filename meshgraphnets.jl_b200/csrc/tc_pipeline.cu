@@ -339,8 +339,14 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       pp.stage[pp.n_stages++] = node_step(k);
     }
     pp.stage[pp.n_stages++] = de;
-    MGN_CUDA_TRY(mlp_forward_persist_tc(pp, std::max(node_tiles, g->n_edge_tiles), st));
-    return MGN_OK;
+    const cudaError_t ce = mlp_forward_persist_tc(pp, std::max(node_tiles, g->n_edge_tiles), st);
+    if (ce != cudaErrorCooperativeLaunchTooLarge) {
+      MGN_CUDA_TRY(ce);
+      return MGN_OK;
+    }
+    // Not every CTA can be resident (the process owns only part of the GPU: MPS thread percentage, a green context):
+    // clear the launch error and run the pass with one launch per MLP below (the weights are packed again: harmless).
+    (void)cudaGetLastError();
   }
 
   if (all || stage == MGN_STAGE_ENCODE) {
