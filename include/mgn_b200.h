@@ -68,7 +68,8 @@ typedef struct mgn_model_config {
   int32_t ln_scale_first; /* LayerNorm parameter order in the flat vector: 0 = (bias, scale) (recalled Lux 0.5
                           * ComponentArray order), 1 = (scale, bias)                                              */
   int32_t aggregate_post_residual; /* 0 = scatter-sum the NEW messages m (DeepMind / recalled GraphNetCore order);
-                          * 1 = scatter-sum ef + m: not built - MGN_ERR_UNSUPPORTED names the kernels to change    */
+                          * 1 = scatter-sum the updated edge latent ef + m (both arithmetic modes, forward and
+                          * backward: the aggregation adjoint then also flows down the edge residual path)         */
 } mgn_model_config;
 
 /* One tensor of the flat Float32 parameter vector (mirrors the ComponentArray `mgn.ps` that

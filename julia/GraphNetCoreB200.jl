@@ -19,7 +19,7 @@ struct MgnConfig            # mirrors mgn_model_config (ABI version 2)
     mps::Int32; hidden_layers::Int32; ln_eps::Float32; compute_mode::Int32
     dense_layers::Int32            # 0 = hidden_layers + 2 (recalled build_mlp)
     ln_scale_first::Int32          # 0 = LayerNorm (bias, scale) order in the flat vector (recalled Lux 0.5)
-    aggregate_post_residual::Int32 # 0 = scatter-sum the new messages (recalled); 1 is not built
+    aggregate_post_residual::Int32 # 0 = scatter-sum the new messages (recalled); 1 = scatter-sum the updated edge latent
 end
 
 # `mgn.ps` is a ComponentArray (src/MeshGraphNets.jl:288,376; handed to ODEProblem at src/strategies.jl:187): the library

@@ -294,11 +294,8 @@ int32_t mgn_model_create(const mgn_model_config* cfg, mgn_model** out) {
   MGN_REQUIRE(cfg->dense_layers == 0 || (cfg->dense_layers >= 2 && cfg->dense_layers <= kMaxDense),
               "model_create: dense_layers must be 0 (= hidden_layers + 2) or in [2, 8]");
   MGN_REQUIRE(cfg->ln_scale_first == 0 || cfg->ln_scale_first == 1, "model_create: ln_scale_first must be 0 or 1");
-  if (cfg->aggregate_post_residual != 0)
-    return fail(MGN_ERR_UNSUPPORTED,
-                "model_create: aggregate_post_residual = 1 is not built: the aggregation would have to run after the "
-                "residual add (segsum_tile call in mlp_fwd_kernel / segment_sum in pipeline.cu) and the edge MLP's "
-                "backward head would have to route d_agg[recv] into the residual path as well (run_chain dy_b16)");
+  MGN_REQUIRE(cfg->aggregate_post_residual == 0 || cfg->aggregate_post_residual == 1,
+              "model_create: aggregate_post_residual must be 0 or 1");
   MGN_REQUIRE(cfg->compute_mode == MGN_COMPUTE_FP32 || cfg->compute_mode == MGN_COMPUTE_BF16,
               "model_create: unknown compute_mode");
   if (cfg->compute_mode == MGN_COMPUTE_BF16)

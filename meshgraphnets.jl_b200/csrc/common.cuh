@@ -232,7 +232,8 @@ cudaError_t node_grad_gather(const float* base, const float* add, int ld_add, co
                              cudaStream_t st);
 // out[r][0:D] = a[r][0:D] + b[r][col_b : col_b + D]
 cudaError_t add_cols(const float* a, const float* b, int ldb, int col_b, int64_t M, int D,
-                     float* out, cudaStream_t st);
+                     float* out, cudaStream_t st, const float* g = nullptr, int ldg = 0, int col_g = 0,
+                     const int32_t* idx = nullptr);   // + g[idx[r], col_g : col_g + D] when g != nullptr
 cudaError_t loss_mse_masked(const float* out, const float* target, int64_t N, int out_dim,
                             const int32_t* mask, int64_t n_mask, int base, float* loss,
                             float* dout, cudaStream_t st);

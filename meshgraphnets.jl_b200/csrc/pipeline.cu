@@ -225,8 +225,8 @@ int32_t forward_stage(const mgn_model* m, const mgn_graph* g, const float* param
     xe.s[2] = {w.ef[cur], nullptr, D, D};
     MGN_CUDA_TRY(mlp_forward(m->mlps[2 + 2 * k], params, xe, E, saved(2 + 2 * k), eps, w.msg,
                              w.ef[cur], w.ef[nxt], nullptr, st));
-    // aggregate the pre-residual messages (a11)
-    MGN_CUDA_TRY(segment_sum(w.msg, g->row_ptr, N, D, agg, st));
+    // aggregate the pre-residual messages (a11) - or, with aggregate_post_residual, the updated edge latent
+    MGN_CUDA_TRY(segment_sum(m->cfg.aggregate_post_residual ? w.ef[nxt] : w.msg, g->row_ptr, N, D, agg, st));
     // node update (a12)
     Operand xn{};
     xn.nseg = 2;
@@ -297,7 +297,12 @@ int32_t backward_stage(const mgn_model* m, const mgn_graph* g, const float* para
     // d_nf[k] = d_nf[k+1] + d(node MLP)/d(nf) + gathers' adjoints (receiver: CSR, sender: CSC)
     MGN_CUDA_TRY(node_grad_gather(w.d_nf, w.dxn, 2 * D, w.dxe, g->row_ptr, g->col_ptr, g->csc_slot,
                                   N, D, w.d_nf, st));
-    MGN_CUDA_TRY(add_cols(d_ef_valid ? w.d_ef : nullptr, w.dxe, 3 * D, 2 * D, E, D, w.d_ef, st));
+    // residual path of the edge latent; aggregate_post_residual: agg = segsum(ef[k+1]), so d_agg[recv] rides along
+    if (m->cfg.aggregate_post_residual)
+      MGN_CUDA_TRY(add_cols(d_ef_valid ? w.d_ef : nullptr, w.dxe, 3 * D, 2 * D, E, D, w.d_ef, st, w.dxn, 2 * D, D,
+                            g->recv_csr));
+    else
+      MGN_CUDA_TRY(add_cols(d_ef_valid ? w.d_ef : nullptr, w.dxe, 3 * D, 2 * D, E, D, w.d_ef, st));
   }
   if (all || stage == MGN_STAGE_ENCODE) {
     if (mps > 0) {

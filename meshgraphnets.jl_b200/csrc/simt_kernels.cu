@@ -475,13 +475,18 @@ node_grad_gather_kernel(const float* __restrict__ base, const float* __restrict_
   }
 }
 
+// out = a + b[:, col_b : col_b + D] (+ g[idx[r], col_g : col_g + D] when g != nullptr: the gathered third term is the
+// aggregation adjoint on the residual path of aggregate_post_residual = 1)
 __global__ void add_cols_kernel(const float* __restrict__ a, const float* __restrict__ b, int ldb,
-                                int col_b, int64_t M, int D, float* __restrict__ out) {
+                                int col_b, int64_t M, int D, float* __restrict__ out, const float* __restrict__ g,
+                                int ldg, int col_g, const int32_t* __restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * D) return;
   const int64_t r = i / D;
   const int c = (int)(i - r * D);
-  out[i] = (a ? a[i] : 0.f) + b[r * ldb + col_b + c];
+  float v = (a ? a[i] : 0.f) + b[r * ldb + col_b + c];
+  if (g) v += g[(int64_t)idx[r] * ldg + col_g + c];
+  out[i] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -785,10 +790,10 @@ cudaError_t node_grad_gather(const float* base, const float* add, int ld_add, co
 }
 
 cudaError_t add_cols(const float* a, const float* b, int ldb, int col_b, int64_t M, int D,
-                     float* out, cudaStream_t st) {
+                     float* out, cudaStream_t st, const float* g, int ldg, int col_g, const int32_t* idx) {
   if (M == 0) return cudaSuccess;
   { ProfScope ps(TAG_ADD_COLS, st);
-  add_cols_kernel<<<blocks_for(M * D, 256), 256, 0, st>>>(a, b, ldb, col_b, M, D, out); }
+  add_cols_kernel<<<blocks_for(M * D, 256), 256, 0, st>>>(a, b, ldb, col_b, M, D, out, g, ldg, col_g, idx); }
   return cudaGetLastError();
 }
 

@@ -99,6 +99,7 @@ struct FwdCore {
   __nv_bfloat16* lat_bf16_out;        // bf16 shadow of lat_out (row-major) ...
   __nv_bfloat16* lat_img_out;         // ... or, when non-null, as tile images (one 32 KB bulk store per tile)
   __nv_bfloat16* agg_bf16;            // [nodes][128]
+  int agg_post_residual;              // FIN_LN_RESID_AGG: aggregate the updated latent (residual added) instead of the message
   float* out;                         // FIN_LINEAR: [rows][out_dim]
   int out_dim;
   const float* val_mask;              // FIN_LINEAR: `.* val_mask` [rows][out_dim] (nullable)   <- src/solve.jl:218
@@ -164,6 +165,8 @@ struct ChainParams {
   int nsteps;                          // 1..kMaxSteps
   const __nv_bfloat16* h_img[kMaxSteps];   // step j: H_{l-1} image
   const __nv_bfloat16* wt_img[kMaxSteps];  // step j: W_l^T image (2 tiles)
+  __nv_bfloat16* dy_out_img;           // optional: dy (as used by the head) written back as a bf16 tile image - in place over
+                                       // dy_a_img: with aggregate_post_residual the residual path carries d_ef + d_agg[recv]
   __nv_bfloat16* dz_out;               // image of the last dZ
   float* partial;                      // [grid][chain_partial_floats(nsteps)]
   unsigned long long* trace;           // debug (see FwdParams::trace)

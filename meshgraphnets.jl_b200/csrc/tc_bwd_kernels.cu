@@ -514,6 +514,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_bwd_chain_kernel(const ChainP
                 dy[2 * e] = __uint_as_float(aw[e] << 16) + __uint_as_float(cw[e] << 16);
                 dy[2 * e + 1] = __uint_as_float(aw[e] & 0xffff0000u) + __uint_as_float(cw[e] & 0xffff0000u);
               }
+              // aggregate_post_residual: the residual path of the edge latent carries d_ef + d_agg[recv] too - written back
+              // over the gradient image (same thread, same 16 bytes it read), where the input kernel's sink picks it up
+              if (p.dy_out_img != nullptr && i < cnt)
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.dy_out_img) + (size_t)tile * kImg + (cc >> 3) * kTileB +
+                                          t128_off(i, cc & 7)) =
+                    make_uint4(pack_bf16x2(dy[0], dy[1]), pack_bf16x2(dy[2], dy[3]), pack_bf16x2(dy[4], dy[5]),
+                               pack_bf16x2(dy[6], dy[7]));
             } else {
               dy[0] = a0[k].x; dy[1] = a0[k].y; dy[2] = a0[k].z; dy[3] = a0[k].w;
               dy[4] = a1[k].x; dy[5] = a1[k].y; dy[6] = a1[k].z; dy[7] = a1[k].w;

@@ -639,28 +639,30 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
         //      aggregation is shared-memory bound, so it runs BEFORE the copy-out's burst of global stores fills
         //      the SM's memory pipeline.
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C0: xhat bulk store issued
-        if (write_lat) {
+        // aggregate_post_residual (mgn_model_config): the aggregation sums the UPDATED edge latent ef + m, so the copy-out
+        // (in place, in the staged tile) comes first and the segmented sum reads its result - also in the last MP step,
+        // whose latent is not written anywhere
+        const bool post = p.fin_mode == FIN_LN_RESID_AGG && p.agg_post_residual != 0;
+        if (write_lat || post) {
           issue_residual(0, 0);
           if constexpr (kResImg) issue_residual(1, 0);   // half of the tile's rows hide behind the aggregation (as many
                                                          // registers as one fp32 batch); the other half is requested at the
                                                          // start of the copy-out, two batches ahead of its use
         }
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C1: first residual batch issued
-        if (p.fin_mode == FIN_LN_RESID_AGG) {
-          const int n0 = rp_s[130], nn = rp_s[131];
-          __nv_bfloat16* agg = p.agg_bf16 + (int64_t)n0 * 128;
-          segsum_tile<true, (EW == 8 ? 4 : 3)>(s_h, s_base + kSmemRp, nn, tid, ln_s, ln_s + 128,
-                            [&](int v, int col0, const float (&a)[8]) {
-                              uint4 o;
-                              o.x = pack_bf16x2(a[0], a[1]);
-                              o.y = pack_bf16x2(a[2], a[3]);
-                              o.z = pack_bf16x2(a[4], a[5]);
-                              o.w = pack_bf16x2(a[6], a[7]);
-                              *reinterpret_cast<uint4*>(agg + (int64_t)v * 128 + col0) = o;
-                            });
-        }
+        __nv_bfloat16* const agg = p.fin_mode == FIN_LN_RESID_AGG ? p.agg_bf16 + (int64_t)rp_s[130] * 128 : nullptr;
+        auto agg_flush = [&](int v, int col0, const float (&a)[8]) {
+          uint4 o;
+          o.x = pack_bf16x2(a[0], a[1]);
+          o.y = pack_bf16x2(a[2], a[3]);
+          o.z = pack_bf16x2(a[4], a[5]);
+          o.w = pack_bf16x2(a[6], a[7]);
+          *reinterpret_cast<uint4*>(agg + (int64_t)v * 128 + col0) = o;
+        };
+        if (p.fin_mode == FIN_LN_RESID_AGG && !post)
+          segsum_tile<true, (EW == 8 ? 4 : 3)>(s_h, s_base + kSmemRp, rp_s[131], tid, ln_s, ln_s + 128, agg_flush);
         if (tid == 0) trace_ev(p.trace, 0, tn);  // C: aggregation done
-        const bool img_out = write_lat && p.lat_img_out != nullptr;
+        const bool img_out = (write_lat && p.lat_img_out != nullptr) || post;   // the new latent is formed in the staged tile
         if (img_out) {
           // the bf16 shadow of the new latent overwrites the xhat tile in place (same thread, same 16 bytes) and leaves as
           // one bulk store: every reader of xhat (aggregation, the xhat save) must be done first
@@ -672,7 +674,7 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
         }
         // ---- copy-out: m = xhat * scale + bias ; residual ; fp32 master + bf16 shadow (coalesced), four batches of
         //      32 rows, the residual rows of batch k+1 in flight while batch k is written
-        if (write_lat) {
+        if (write_lat || post) {
           if constexpr (kResImg) {
             issue_residual(2, 0);
             issue_residual(3, 0);
@@ -730,11 +732,13 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
         if (img_out) {
           fence_proxy_async();
           named_bar_sync(1, kEpi);
-          if (tid == 0) {
+          if (tid == 0 && p.lat_img_out != nullptr) {
             bulk_s2g(reinterpret_cast<uint8_t*>(p.lat_img_out) + (size_t)tile * 2 * kTileB, s_h, 2 * kTileB);
             bulk_commit();
             store_pending = true;
           }
+          if (post)   // rows >= cnt of the tile are zero and belong to no node
+            segsum_tile<false, (EW == 8 ? 4 : 3)>(s_h, s_base + kSmemRp, rp_s[131], tid, nullptr, nullptr, agg_flush);
         }
         if (tid == 0) trace_ev(p.trace, 2, tn);  // E3: copy-out + aggregation done (this thread)
       }

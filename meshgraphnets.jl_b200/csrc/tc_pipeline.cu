@@ -273,6 +273,8 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
       p.lat_img_in = w.ef16[cur];   // residual = the bf16 latent itself (in place when not training: tile-local)
       p.lat_img_out = w.ef16[nxt];
     }
+    p.agg_post_residual = m->cfg.aggregate_post_residual;
+    if (p.agg_post_residual) p.lat_img_in = w.ef16[cur];   // ... but the aggregation of the last step still sums ef + m
     p.agg_bf16 = w.agg16[training ? k : 0];
     return p;
   };
@@ -440,7 +442,8 @@ int32_t join_lane(const BwdCtx& c) {
 // Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
 // LayerNorm (dy = dy_a[r], or dy_a_img[r] + dy_b16[b_idx[r]] for edge rows); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
 int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const __nv_bfloat16* dy_b16,
-                  const int32_t* b_idx, Pieces& pc, const __nv_bfloat16* dy_a_img = nullptr) {
+                  const int32_t* b_idx, Pieces& pc, const __nv_bfloat16* dy_a_img = nullptr,
+                  __nv_bfloat16* dy_out_img = nullptr) {
   const MlpLayout& L = c.m->mlps[mi];
   const MlpImages& im = c.m->images->mlps[mi];
   const MlpSave& sv = c.w->saves[mi];
@@ -454,6 +457,7 @@ int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a,
     p.head_mode = HEAD_LN;
     p.dy_a = dy_a;
     p.dy_a_img = dy_a_img;
+    p.dy_out_img = dy_out_img;
     p.dy_b16 = dy_b16;
     p.b_idx = b_idx;
     p.xhat = sv.xhat;
@@ -588,7 +592,11 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       const size_t mi = 2 + 2 * k;
       Pieces pc{};
       MGN_TRY(begin_mlp(c));
-      MGN_TRY(run_chain(c, mi, true, nullptr, b.d_agg, g->recv_csr, pc, d_ef_valid ? b.d_ef : nullptr));
+      // aggregate_post_residual: agg = segsum(ef[k+1]), so the residual path carries d_ef + d_agg[recv] as well: the chain
+      // head writes that sum back over the gradient image and the input kernel's sink adds dX to it
+      const bool post = m->cfg.aggregate_post_residual != 0;
+      MGN_TRY(run_chain(c, mi, true, nullptr, b.d_agg, g->recv_csr, pc, d_ef_valid ? b.d_ef : nullptr,
+                        post ? b.d_ef : nullptr));
       InputParams p{};
       p.n_tiles = g->n_edge_tiles;
       p.M = E;
@@ -607,7 +615,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       p.sink[1] = SINK_SEGSUM_F32;  // receiver adjoint: CSR segments are tile-local; plain stores, added to d_nf by the
       p.f32_dst[1] = b.recv_sum;    // gather below
       p.sink[2] = SINK_ADD_IMG;     // edge-latent residual: d_ef = bf16(d_ef + dX), tile images, in place
-      p.img_src[2] = d_ef_valid ? b.d_ef : nullptr;
+      p.img_src[2] = (d_ef_valid || post) ? b.d_ef : nullptr;
       p.bf16_dst[2] = b.d_ef;
       MGN_TRY(run_input(c, mi, p, pc));
       MGN_CUDA_TRY(sender_gather_add(b.d_nf, b.recv_sum, b.dxs, g->col_ptr, g->csc_pos, N, st, m->knobs.pdl != 0));

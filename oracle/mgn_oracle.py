@@ -243,6 +243,7 @@ class ModelConfig:
     # the recalled internals as switches (mgn_model_config of include/mgn_b200.h)
     dense_layers: int = 0          # 0 = hidden_layers + 2
     ln_scale_first: bool = False   # flat order of the LayerNorm parameters: (bias, scale) recalled
+    aggregate_post_residual: bool = False   # False: agg = scatter(+, m) (DeepMind order, recalled); True: scatter(+, ef + m)
 
     @property
     def n_dense(self):
@@ -372,7 +373,8 @@ def model_forward(cfg: ModelConfig, params, nf, ef, senders, receivers, index_ba
     """``mgn.model(graph, ps, st)`` as called at src/solve.jl:200 / inside step!
     (src/strategies.jl:421): Encoder -> mps x Processor -> Decoder.
     Processor (recalled, DeepMind order): m = LN(MLP_e([nf[s]; nf[r]; ef])),
-    agg = scatter(+, m, r) (pre-residual), n = LN(MLP_n([nf; agg])), nf += n, ef += m."""
+    agg = scatter(+, m, r) (pre-residual), n = LN(MLP_n([nf; agg])), nf += n, ef += m.
+    ``cfg.aggregate_post_residual`` is the other reading of the block: agg = scatter(+, ef + m, r)."""
     dtype = dtype or params.dtype
     p = params.astype(dtype, copy=False)
     nf = np.asarray(nf, dtype=dtype)
@@ -386,7 +388,7 @@ def model_forward(cfg: ModelConfig, params, nf, ef, senders, receivers, index_ba
     for k in range(cfg.mps):
         se, sn = specs[2 + 2 * k], specs[3 + 2 * k]
         m = _mlp_forward(p, se, np.concatenate([x[s0], x[r0], e], axis=1), cfg.ln_eps, tape)
-        agg = scatter_add(m, r0, N)
+        agg = scatter_add(e + m if cfg.aggregate_post_residual else m, r0, N)
         n = _mlp_forward(p, sn, np.concatenate([x, agg], axis=1), cfg.ln_eps, tape)
         x = x + n
         e = e + m
@@ -411,6 +413,8 @@ def model_backward(cfg: ModelConfig, params, tape, dout, senders, receivers, n_n
         dx = dx + din[:, :D]
         dagg = din[:, D:]
         dm = de + dagg[r0]                                     # ef' = ef + m ; agg = scatter(m)
+        if cfg.aggregate_post_residual:                        # agg = scatter(ef'): the aggregation adjoint also flows
+            de = dm                                            # down the residual path
         din = _mlp_backward(p, g, rec_e, dm)
         np.add.at(dx, s0, din[:, :D])
         np.add.at(dx, r0, din[:, D:2 * D])

@@ -33,9 +33,25 @@ def test_backward_matches_autograd_fp64():
     assert np.allclose(tnf.grad.numpy(), dnf, rtol=1e-9, atol=1e-12)
 
 
-def test_backward_matches_finite_differences():
-    cfg, p, nf, ef, s, r, tgt, mask = _problem(seed=1, D=8, mps=1, nx=4, ny=3)
-    g, loss, _, _ = orc.step(cfg, p, nf, ef, s, r, tgt, mask)
+import pytest
+
+
+@pytest.mark.parametrize("post", [False, True])
+def test_backward_matches_finite_differences(post):
+    """Both readings of the aggregation order (mgn_model_config::aggregate_post_residual)."""
+    cfg, p, nf, ef, s, r, tgt, mask = _problem(seed=1, D=8, mps=2 if post else 1, nx=4, ny=3)
+    cfg.aggregate_post_residual = post
+    g, loss, _, dnf = orc.step(cfg, p, nf, ef, s, r, tgt, mask)
+    if post:   # the switch changes the function ...
+        cfg0 = orc.ModelConfig(**{**cfg.__dict__, "aggregate_post_residual": False})
+        assert abs(orc.step(cfg0, p, nf, ef, s, r, tgt, mask)[1] - loss) > 1e-6
+        # ... and d loss / d node features is checked too (the NeuralODE adjoint consumes it)
+        i, j = 3, 2
+        x = nf.copy(); x[i, j] += 1e-6
+        lp = orc.step(cfg, p, x, ef, s, r, tgt, mask)[1]
+        x[i, j] -= 2e-6
+        lm = orc.step(cfg, p, x, ef, s, r, tgt, mask)[1]
+        assert abs((lp - lm) / 2e-6 - dnf[i, j]) < 1e-6 * max(1.0, abs(dnf[i, j]))
     rng = np.random.default_rng(5)
     nz = np.nonzero(g)[0]
     for i in rng.choice(nz, 12, replace=False):
