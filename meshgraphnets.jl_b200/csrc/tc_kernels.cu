@@ -509,6 +509,60 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
             // LayerNorm statistics: sums of the data shifted by the row's first element (the shifted-data formula keeps the
             // fp32 variance accurate), biased variance; sums over the left and the right 64 columns separately, in column
             // order, then added: the same arithmetic for both thread layouts (mirrored by oracle/mgn_oracle_bf16.py)
+            if constexpr (RING == kRingDeep) {
+              // One CTA per SM (small graphs, persistent kernel): registers abound, so the thread's 64 columns are loaded
+              // ONCE, stay in registers between the statistics and the normalisation, and the accumulator is released to
+              // the MMA warp before the statistics are even exchanged.  Same arithmetic, same bits as the two-pass form.
+              uint32_t ra[32], rb[32], r_first;
+              tmem_ld1_issue(t_lane, r_first);
+              tmem_ld32_issue(t_lane + c_lo * 32, ra);
+              tmem_ld32_issue(t_lane + (c_lo + 1) * 32, rb);
+              tmem_ld_wait();
+              tmem_regs_fence(ra);
+              tmem_regs_fence(rb);
+              const float shift = __uint_as_float(r_first) + bias_s[l * 128];
+              float s = 0.f, q = 0.f;
+#pragma unroll
+              for (int cc2 = 0; cc2 < 2; ++cc2) {
+                uint32_t* r = cc2 == 0 ? ra : rb;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                  const float4 b4 = ld_shared_f4(bs + (uint32_t)(cc2 * 128 + g * 16));
+                  const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float vb = __uint_as_float(r[4 * g + e]) + bb[e];
+                    r[4 * g + e] = __float_as_uint(vb);
+                    const float d = vb - shift;
+                    s += d;
+                    q = fmaf(d, d, q);
+                  }
+                }
+              }
+              tc_fence_before();
+              mbar_arrive(epi_done);   // TMEM is drained: the MMA warp may start the next tile / stage
+              arrived = true;
+              stat_s[half * 128 + row] = make_float2(s, q);
+              named_bar_sync(1, kEpi);   // also the barrier in front of the stores into the tile (thread 0 waited in pre_bar)
+              post_bar();
+              const float2 a = stat_s[row], b = stat_s[128 + row];
+              s = a.x + b.x;
+              q = a.y + b.y;
+              const float ms = s * (1.f / 128.f);
+              mean = shift + ms;
+              q = fmaxf(q * (1.f / 128.f) - ms * ms, 0.f) * 128.f;
+              rstd = 1.f / sqrtf(q * (1.f / 128.f) + p.eps);
+              if (p.save_rstd && row < cnt && half == 0) p.save_rstd[row0 + row] = rstd;
+#pragma unroll
+              for (int cc2 = 0; cc2 < 2; ++cc2) {
+                const uint32_t* r = cc2 == 0 ? ra : rb;
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  w[j] = pack_bf16x2((__uint_as_float(r[2 * j]) - mean) * rstd, (__uint_as_float(r[2 * j + 1]) - mean) * rstd);
+                store_chunk(c_lo + cc2, w);
+              }
+            } else {
             // (the 64 columns do not fit in registers beside the loop state at 96 registers per thread: TMEM is read twice)
             uint32_t r[32], r_first;
             float shift = 0.f, s = 0.f, q = 0.f;
@@ -555,6 +609,7 @@ __device__ __forceinline__ void fwd_body(const FwdCore& p, const FeatRecipe& fea
                 w[2 * g + 1] = pack_bf16x2((__uint_as_float(r[4 * g + 2]) + b4.z - mean) * rstd, (__uint_as_float(r[4 * g + 3]) + b4.w - mean) * rstd);
               }
               store_chunk(c_lo + cc2, w);
+            }
             }
           }
         } else {
