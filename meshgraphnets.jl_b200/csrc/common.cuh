@@ -81,6 +81,8 @@ struct TuneKnobs {
   int fwd_deep_ring = 1;   // MGN_FWD_DEEP_RING=0 disables the deep-ring variant for small graphs
   int fwd_persist = 1;     // inference pass of a graph with no more tiles than SMs as ONE persistent cooperative launch:
                            // MGN_FWD_PERSIST=0 never, 1 unless the call is being captured into a CUDA graph, 2 always
+  int recompute = 0;       // MGN_RECOMPUTE=1: no activation saves of the processor MLPs in the forward pass; the backward pass
+                           // re-runs each MLP for them (5x less workspace per edge row and MP step, ~1.3x the step time)
   int reduce_lane = 1;     // MGN_REDUCE_LANE=0: reduce the weight-gradient partials inline on the caller's stream
   int pdl = 0;             // MGN_PDL=1: programmatic dependent launch between the library's kernels (measured: no gain
                            // inside a CUDA graph, -3 % on the 32-window step; kept as an opt-in for eager callers)

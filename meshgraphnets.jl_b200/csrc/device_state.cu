@@ -94,6 +94,7 @@ TuneKnobs read_tune_knobs() {
   if (const char* e = getenv("MGN_FWD_STAGGER_NS")) k.fwd_stagger_ns = atoi(e) > 0 ? atoi(e) : 0;
   if (const char* e = getenv("MGN_FWD_DEEP_RING")) k.fwd_deep_ring = atoi(e) == 0 ? 0 : 1;
   if (const char* e = getenv("MGN_FWD_PERSIST")) k.fwd_persist = atoi(e) == 0 ? 0 : (atoi(e) == 2 ? 2 : 1);
+  if (const char* e = getenv("MGN_RECOMPUTE")) k.recompute = atoi(e) == 1 ? 1 : 0;
   if (const char* e = getenv("MGN_REDUCE_LANE")) k.reduce_lane = atoi(e) == 0 ? 0 : 1;
   if (const char* e = getenv("MGN_PDL")) k.pdl = atoi(e) == 1 ? 1 : 0;
   return k;

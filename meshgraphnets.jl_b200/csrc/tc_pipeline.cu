@@ -75,13 +75,29 @@ void tc_layout(const mgn_model* m, const mgn_graph* g, bool training, void* base
   for (auto& a : w.agg16) a = b.h((size_t)N * 128);
   w.saves.resize(m->mlps.size());
   if (training) {
+    // MGN_RECOMPUTE=1 (TuneKnobs::recompute): the processor MLPs write no activation saves in the forward pass; the
+    // backward pass re-runs an MLP (FIN_LN form: saves only) right before its own kernels, into ONE save set per kind of
+    // MLP - 1 284 B per edge row and MP step less workspace (only the bf16 latents of every step stay), one extra MLP
+    // forward per MLP and step of time.  The recomputed saves are the same bits, so are the gradients.
+    const size_t first_proc = 2, last_proc = m->mlps.size() - 1;   // [first_proc, last_proc): (edge, node) x mps
+    MlpSave shared[2];
+    bool have_shared[2] = {false, false};   // (the pointers are null when only the size is computed)
     for (size_t i = 0; i < m->mlps.size(); ++i) {
       const bool edge = is_edge_mlp(m, i);
+      const bool proc = i >= first_proc && i < last_proc;
+      if (proc && m->knobs.recompute && have_shared[edge ? 0 : 1]) {
+        w.saves[i] = shared[edge ? 0 : 1];
+        continue;
+      }
       const int64_t tiles = edge ? edge_tiles : node_tiles, rows = edge ? E : N;
       for (int l = 0; l < L - 1; ++l) w.saves[i].h[l] = static_cast<__nv_bfloat16*>(b.raw((size_t)tiles * 2 * kTileB));
       if (m->mlps[i].layer_norm) {
         w.saves[i].xhat = static_cast<__nv_bfloat16*>(b.raw((size_t)tiles * 2 * kTileB));
         w.saves[i].rstd = b.f((size_t)std::max<int64_t>(rows, 1));
+      }
+      if (proc && m->knobs.recompute) {
+        shared[edge ? 0 : 1] = w.saves[i];
+        have_shared[edge ? 0 : 1] = true;
       }
     }
   }
@@ -225,6 +241,11 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
   const bool all = stage == kStageAll;
 
   // ---- the FwdParams of every MLP of the pass
+  auto no_saves = [](FwdParams& p) {   // MGN_RECOMPUTE: the backward pass re-runs the processor MLPs for their saves
+    for (int l = 0; l < kMaxLayers - 1; ++l) p.save_h[l] = nullptr;
+    p.save_xhat = nullptr;
+    p.save_rstd = nullptr;
+  };
   auto enc_node = [&]() {   // Encoder (a9): raw fp32 features -> latent
     FwdParams p{};
     fill_layers(m, 0, params, w, training, p);
@@ -276,6 +297,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
     p.agg_post_residual = m->cfg.aggregate_post_residual;
     if (p.agg_post_residual) p.lat_img_in = w.ef16[cur];   // ... but the aggregation of the last step still sums ef + m
     p.agg_bf16 = w.agg16[training ? k : 0];
+    if (m->knobs.recompute) no_saves(p);
     return p;
   };
   auto node_step = [&](int k) {   // node update + residual (a12)
@@ -291,6 +313,7 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
     p.lat_in = w.nf32;
     p.lat_out = w.nf32;
     p.lat_bf16_out = w.nf16[nxt];
+    if (m->knobs.recompute) no_saves(p);
     return p;
   };
   auto decoder = [&]() {   // Decoder (a13)
@@ -439,6 +462,35 @@ int32_t join_lane(const BwdCtx& c) {
   return MGN_OK;
 }
 
+// MGN_RECOMPUTE: the saves (hidden activations, xhat, rstd) of processor MLP `mi` of MP step k are produced again - the MLP
+// in its FIN_LN form, same operands as in the forward pass (the bf16 latents of every step are kept), no latent outputs.
+int32_t recompute_saves(const BwdCtx& c, int k, bool edge) {
+  const mgn_model* m = c.m;
+  const mgn_graph* g = c.g;
+  const size_t mi = (edge ? 2 : 3) + 2 * (size_t)k;
+  FwdParams p{};
+  fill_layers(m, mi, c.params, *c.w, true, p);
+  p.fin_mode = FIN_LN;
+  if (edge) {
+    p.n_tiles = g->n_edge_tiles;
+    p.M = g->E;
+    p.tile_row_start = g->tile_row_start;
+    p.in_mode = IN_GATHER3;
+    p.x0 = c.w->nf16[k];
+    p.x2_img = c.w->ef16[k];
+    p.idx0 = g->send_csr;
+    p.idx1 = g->recv_csr;
+  } else {
+    p.n_tiles = (int)((g->N + kTile - 1) / kTile);
+    p.M = g->N;
+    p.in_mode = IN_CONCAT2;
+    p.x0 = c.w->nf16[k];
+    p.x1 = c.w->agg16[k];
+  }
+  MGN_CUDA_TRY(mlp_forward_tc(p, c.st));
+  return MGN_OK;
+}
+
 // Chain kernel + fixed-order reduction of its partials for MLP `mi`.  HEAD_LN when the MLP ends in a
 // LayerNorm (dy = dy_a[r], or dy_a_img[r] + dy_b16[b_idx[r]] for edge rows); HEAD_IMAGE for the decoder (top dZ precomputed in b->ztop).
 int32_t run_chain(const BwdCtx& c, size_t mi, bool edge_rows, const float* dy_a, const __nv_bfloat16* dy_b16,
@@ -574,6 +626,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       const size_t mi = 3 + 2 * k;
       Pieces pc{};
       MGN_TRY(begin_mlp(c));
+      if (m->knobs.recompute) MGN_TRY(recompute_saves(c, k, false));
       MGN_TRY(run_chain(c, mi, false, b.d_nf, nullptr, nullptr, pc));
       InputParams p{};
       p.n_tiles = node_tiles;
@@ -592,6 +645,7 @@ int32_t tc_backward_stage(const mgn_model* m, const mgn_graph* g, const float* p
       const size_t mi = 2 + 2 * k;
       Pieces pc{};
       MGN_TRY(begin_mlp(c));
+      if (m->knobs.recompute) MGN_TRY(recompute_saves(c, k, true));
       // aggregate_post_residual: agg = segsum(ef[k+1]), so the residual path carries d_ef + d_agg[recv] as well: the chain
       // head writes that sum back over the gradient image and the input kernel's sink adds dX to it
       const bool post = m->cfg.aggregate_post_residual != 0;
