@@ -343,7 +343,8 @@ int32_t tc_forward_stage(const mgn_model* m, const mgn_graph* g, const float* pa
   const int n_stages = 3 + 2 * mps;
   bool persist = all && !training && E > 0 && mps >= 1 && m->knobs.fwd_persist != 0 &&
                  forward_persist_ok(std::max(node_tiles, g->n_edge_tiles), n_stages);
-  if (persist && m->knobs.fwd_persist == 1) {
+  if (persist && m->knobs.fwd_persist == 1 && st != nullptr && st != cudaStreamLegacy) {
+    // (the legacy default stream cannot be captured; querying it while another stream captures would invalidate that capture)
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     MGN_CUDA_TRY(cudaStreamIsCapturing(st, &cs));
     persist = cs == cudaStreamCaptureStatusNone;
