@@ -476,6 +476,26 @@ def partition_leg(args, pkg, rank, world, local_rank, comm):
     torch.cuda.synchronize()
     ms_eager = e0.elapsed_time(e1) / K
     ex_ms = sum(a.elapsed_time(b) for a, b in ev) / K
+    # the same event pairs with the ranks aligned on the device right before every exchange (a one-element all-reduce
+    # absorbs the skew): what is left is the transfer itself - concatenation, grouped send / recv - without the wait for
+    # the slowest peer that the figure above includes
+    ev_sync, skew = [], torch.zeros(1, device=dev)
+
+    def aligned_exchange(sends, direction):
+        if comm is not None:
+            comm.allreduce_sum_(skew)
+        else:
+            dist.all_reduce(skew)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = base(sends, direction)
+        b.record()
+        ev_sync.append((a, b))
+        return out
+
+    step(aligned_exchange)
+    torch.cuda.synchronize()
+    ex_sync_ms = sum(a.elapsed_time(b) for a, b in ev_sync)
     # the same step - 33 stages, 29 halo exchanges, 2 all-reduces - captured once and replayed as ONE CUDA graph
     ms, captured = ms_eager, False
     try:
@@ -501,14 +521,16 @@ def partition_leg(args, pkg, rank, world, local_rank, comm):
         print(f"[bench] partitioned step: CUDA graph capture failed ({e!r}); eager launches", file=sys.stderr)
         torch.cuda.synchronize()
     halo = sum(len(v) for v in part.recv_rows.values())
-    tt = torch.tensor([ms, ex_ms, float(halo), float(len(part.edge_ids)), ms_eager], device=dev, dtype=torch.float64)
+    tt = torch.tensor([ms, ex_ms, float(halo), float(len(part.edge_ids)), ms_eager, ex_sync_ms], device=dev,
+                      dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ws_gb = model.workspace_bytes(pm.graph.index, True) / 1e9
     lat_b, grad_b = model.halo_row_bytes(pkg.HALO_LATENT), model.halo_row_bytes(pkg.HALO_GRAD)
     return {"workload": f"kuhn_tet_grid_{n}^3_partitioned_train_step", "nodes": N, "edges": E, "mps": MPS,
             "ms_per_step": float(tt[0]), "mp_step_edges_per_sec": E * MPS / (float(tt[0]) * 1e-3),
             "cuda_graph": captured, "ms_per_step_eager": float(tt[4]),
-            "exchange_ms_per_step_max_rank": float(tt[1]), "exchanges_per_step": 2 * MPS - 1,
+            "exchange_ms_per_step_max_rank": float(tt[1]), "exchange_ms_per_step_ranks_aligned": float(tt[5]),
+            "exchanges_per_step": 2 * MPS - 1,
             "halo_rows_max_rank": int(tt[2]), "edges_max_rank": int(tt[3]),
             "halo_bytes_per_step_max_rank": int(tt[2]) * ((MPS - 1) * lat_b + MPS * grad_b),
             "workspace_gb_rank0": ws_gb, "steps": K,
